@@ -1,0 +1,757 @@
+"""CPU oracle for the Grad-Shafranov hot path (TEST INFRASTRUCTURE, not product).
+
+A plain-NumPy restatement of the reference's lane-A algorithm,
+written from the reference's behaviour, one function per reference function and
+each citing the reference file:line it follows (paths relative to the
+reference root).  Only ``tests/``, ``__graft_entry__.smoke()`` and the
+``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import this
+module; the product path (``scpn_fusion_core_b200``) never does.
+
+Pinning: ``tests/golden/make_golden.py`` runs the UNMODIFIED reference in the
+build container and commits its outputs under ``tests/golden/``;
+``tests/test_oracle_vs_golden.py`` checks every function here against them
+(bit-exact for the element-wise operators, <=1e-13 for the full Picard solve).
+The lane-C plasma->wall response matrix (``wall_response_matrix``) has no
+runnable reference here (jax absent): that single function is "parity unpinned"
+by a reference run and pinned only through scipy's Cephes ``ellipk/ellipe``.
+
+All fields are float64, C-order, shape (nz, nr), index [iz, ir].
+"""
+from __future__ import annotations
+
+import math
+import time
+from typing import Any
+
+import numpy as np
+
+SANITIZE_CAP = 1.0e250  # src/scpn_fusion/core/fusion_kernel_numerics.py:16
+MU0_SI = 4e-7 * np.pi  # src/scpn_fusion/core/fusion_kernel_free_boundary.py:27
+
+
+# --------------------------------------------------------------------------
+# multigrid free functions  (src/scpn_fusion/core/multigrid_solve.py)
+# --------------------------------------------------------------------------
+
+def check_omega(omega: float) -> float:
+    """multigrid_solve.py:33-54 - omega finite and in [1, 2)."""
+    w = float(omega)
+    if not math.isfinite(w) or w < 1.0 or w >= 2.0:
+        raise ValueError("omega must be finite and satisfy 1.0 <= omega < 2.0")
+    return w
+
+
+def restrict_full_weight(fine: np.ndarray) -> np.ndarray:
+    """multigrid_solve.py:57-99 - 9-point full weighting, walls injected.
+
+    Coarse size is (n+1)//2 per axis.  Operand order of the reference is kept
+    (4*c + 2*(S+N+W+E) + (SW+SE+NW+NE)) / 16 so results are bit-identical.
+    """
+    nzf, nrf = fine.shape
+    nzc, nrc = (nzf + 1) // 2, (nrf + 1) // 2
+    out = np.zeros((nzc, nrc))
+    c = fine[2:-2:2, 2:-2:2]
+    s, n = fine[1:-3:2, 2:-2:2], fine[3:-1:2, 2:-2:2]
+    w, e = fine[2:-2:2, 1:-3:2], fine[2:-2:2, 3:-1:2]
+    sw, se = fine[1:-3:2, 1:-3:2], fine[1:-3:2, 3:-1:2]
+    nw, ne = fine[3:-1:2, 1:-3:2], fine[3:-1:2, 3:-1:2]
+    out[1:-1, 1:-1] = (4.0 * c + 2.0 * (s + n + w + e) + (sw + se + nw + ne)) / 16.0
+    out[0, :] = fine[0, ::2][:nrc]
+    out[-1, :] = fine[-1, ::2][:nrc]
+    out[:, 0] = fine[::2, 0][:nzc]
+    out[:, -1] = fine[::2, -1][:nzc]
+    return out
+
+
+def prolong_bilinear(coarse: np.ndarray, nzf: int, nrf: int) -> np.ndarray:
+    """multigrid_solve.py:102-145 - bilinear interpolation incl. its slicing limits.
+
+    For even fine sizes the last fine row/column receives nothing (stays 0).
+    """
+    nzc, nrc = coarse.shape
+    fine = np.zeros((nzf, nrf))
+    kz = min(nzc, (nzf + 1) // 2)
+    kr = min(nrc, (nrf + 1) // 2)
+    hend = min(2 * (nrc - 1), nrf - 1)
+    vend = min(2 * (nzc - 1), nzf - 1)
+    nh = (hend - 1) // 2 + 1
+    nv = (vend - 1) // 2 + 1
+    fine[: 2 * kz - 1 : 2, : 2 * kr - 1 : 2] = coarse[:kz, :kr]
+    fine[: 2 * kz - 1 : 2, 1:hend:2] = (0.5 * (coarse[:kz, :-1] + coarse[:kz, 1:]))[:, :nh]
+    fine[1:vend:2, : 2 * kr - 1 : 2] = (0.5 * (coarse[:-1, :kr] + coarse[1:, :kr]))[:nv, :]
+    fine[1:vend:2, 1:hend:2] = (
+        0.25 * (coarse[:-1, :-1] + coarse[1:, :-1] + coarse[:-1, 1:] + coarse[1:, 1:])
+    )[:nv, :nh]
+    return fine
+
+
+def _stencil_coeffs(r_grid: np.ndarray, dr: float, dz: float):
+    """multigrid_solve.py:181-189 - a_e, a_w (interior arrays), a_ns, a_c."""
+    dr2 = dr ** 2
+    dz2 = dz ** 2
+    r_safe = np.maximum(r_grid[1:-1, 1:-1], 1e-10)
+    a_e = 1.0 / dr2 - 1.0 / (2.0 * r_safe * dr)
+    a_w = 1.0 / dr2 + 1.0 / (2.0 * r_safe * dr)
+    a_ns = 1.0 / dz2
+    a_c = 2.0 / dr2 + 2.0 / dz2
+    return a_e, a_w, a_ns, a_c
+
+
+def _colour_slices(nz: int, nr: int, parity: int):
+    """Interior slices of one colour: global (iz+ir) % 2 == parity."""
+    out = []
+    for i0 in (1, 2):
+        j0 = 1 if (i0 + 1) % 2 == parity else 2
+        out.append((slice(i0, nz - 1, 2), slice(j0, nr - 1, 2)))
+    return out
+
+
+def rb_sor_smooth(psi, source, r_grid, dr, dz, omega, n_sweeps, *, clip=False):
+    """multigrid_solve.py:148-208 (mg_smooth) - in-place red-black SOR.
+
+    gs = (a_e*E + a_w*W + a_ns*S + a_ns*N - src) / a_c ; psi = (1-w)*psi + w*gs,
+    colour 0 then colour 1, wall untouched.  Implemented with strided slices
+    instead of the reference's boolean gathers: same element-wise operations in
+    the same order, hence bit-identical.  ``clip`` adds the +-1e250 clamp of
+    fusion_kernel_iterative_solver.py:158 (_sor_step).
+    """
+    omega = check_omega(omega)
+    nz, nr = psi.shape
+    a_e, a_w, a_ns, a_c = _stencil_coeffs(r_grid, dr, dz)
+    for _ in range(int(n_sweeps)):
+        for parity in (0, 1):
+            for zs, rs in _colour_slices(nz, nr, parity):
+                zi = slice(zs.start - 1, nz - 2, 2)  # index into the interior arrays
+                ri = slice(rs.start - 1, nr - 2, 2)
+                east = psi[zs, rs.start + 1 : nr : 2]
+                west = psi[zs, rs.start - 1 : nr - 2 : 2]
+                south = psi[zs.start - 1 : nz - 2 : 2, rs]
+                north = psi[zs.start + 1 : nz : 2, rs]
+                gs = (
+                    a_e[zi, ri] * east + a_w[zi, ri] * west + a_ns * south + a_ns * north
+                    - source[zs, rs]
+                ) / a_c
+                new = (1.0 - omega) * psi[zs, rs] + omega * gs
+                if clip:
+                    new = np.clip(new, -SANITIZE_CAP, SANITIZE_CAP)
+                psi[zs, rs] = new
+    return psi
+
+
+def gs_operator(psi, r_grid, dr, dz):
+    """fusion_kernel_solver_runtime.py:54-68 - L*psi on the interior, 0 on the wall."""
+    out = np.zeros_like(psi)
+    r_safe = np.maximum(r_grid[1:-1, 1:-1], 1e-10)
+    c = psi[1:-1, 1:-1]
+    d2r = (psi[1:-1, 2:] - 2.0 * c + psi[1:-1, 0:-2]) / dr ** 2
+    d1r = (psi[1:-1, 2:] - psi[1:-1, 0:-2]) / (2.0 * dr)
+    d2z = (psi[2:, 1:-1] - 2.0 * c + psi[0:-2, 1:-1]) / dz ** 2
+    out[1:-1, 1:-1] = d2r - d1r / r_safe + d2z
+    return out
+
+
+def gs_residual(psi, source, r_grid, dr, dz):
+    """multigrid_solve.py:211-249 (mg_residual) - r = L*psi - source, 0 on the wall."""
+    out = gs_operator(psi, r_grid, dr, dz)
+    out[1:-1, 1:-1] = out[1:-1, 1:-1] - source[1:-1, 1:-1]
+    return out
+
+
+def vcycle(psi, source, r_grid, dr, dz, *, omega=1.0, pre=3, post=3, min_grid=5):
+    """multigrid_solve.py:252-335 - one recursive V-cycle.
+
+    Base case (min_grid >= nz or nr): 50 sweeps.  Coarse R-grid is the full
+    weighting of the fine R-grid; spacings double; correction is added on the
+    whole array (wall included); the wall is NOT re-applied here.
+    """
+    nz, nr = psi.shape
+    if min_grid >= nz or min_grid >= nr:
+        return rb_sor_smooth(psi.copy(), source, r_grid, dr, dz, omega, 50)
+    psi = rb_sor_smooth(psi.copy(), source, r_grid, dr, dz, omega, pre)
+    defect = -gs_residual(psi, source, r_grid, dr, dz)
+    d_c = restrict_full_weight(defect)
+    r_c = restrict_full_weight(r_grid)
+    e_c = vcycle(np.zeros_like(d_c), d_c, r_c, dr * 2.0, dz * 2.0,
+                 omega=omega, pre=pre, post=post, min_grid=min_grid)
+    psi = psi + prolong_bilinear(e_c, nz, nr)
+    return rb_sor_smooth(psi, source, r_grid, dr, dz, omega, post)
+
+
+def residual_linf(psi, source, r_grid, dr, dz) -> float:
+    """multigrid_solve.py:338-349 - max |r| over the interior."""
+    r = gs_residual(psi, source, r_grid, dr, dz)[1:-1, 1:-1]
+    return float(np.max(np.abs(r))) if r.size else 0.0
+
+
+def copy_wall(dst, src) -> None:
+    """fusion_kernel_iterative_solver.py:316-329 / multigrid_solve.py:437-441."""
+    dst[0, :] = src[0, :]
+    dst[-1, :] = src[-1, :]
+    dst[:, 0] = src[:, 0]
+    dst[:, -1] = src[:, -1]
+
+
+def mg_solve(source, psi_bc, r_min, r_max, z_min, z_max, nr, nz, *, tol=1e-6,
+             max_cycles=500, omega=1.0, pre=3, post=3, min_grid=5):
+    """multigrid_solve.py:352-463 - V-cycles until Linf residual < tol."""
+    src = np.asarray(source, dtype=np.float64)
+    psi = np.asarray(psi_bc, dtype=np.float64).copy()
+    if src.shape != (nz, nr) or psi.shape != (nz, nr):
+        raise ValueError("source and psi_bc must have shape (nz, nr)")
+    if not (np.isfinite(tol) and tol > 0.0):
+        raise ValueError("tol must be finite and > 0.")
+    if max_cycles < 1:
+        raise ValueError("max_cycles must be >= 1.")
+    r_axis = np.linspace(r_min, r_max, nr)
+    z_axis = np.linspace(z_min, z_max, nz)
+    r_grid, _ = np.meshgrid(r_axis, z_axis)
+    dr = float(r_axis[1] - r_axis[0]) if nr > 1 else 1.0
+    dz = float(z_axis[1] - z_axis[0]) if nz > 1 else 1.0
+    wall = psi.copy()
+    n = 0
+    res = residual_linf(psi, src, r_grid, dr, dz)
+    while not res < tol and n < max_cycles:
+        psi = vcycle(psi, src, r_grid, dr, dz, omega=omega, pre=pre, post=post, min_grid=min_grid)
+        copy_wall(psi, wall)
+        n += 1
+        res = residual_linf(psi, src, r_grid, dr, dz)
+    return psi, res, n, bool(res < tol)
+
+
+def provider_rb_sor_smooth(psi, source, r_left, r_right, z_bottom, z_top, *, omega=1.3, n_sweeps=50):
+    """_multi_compat_providers.py:723-752 - the `gs_rb_sor_smooth` NumPy tier.
+
+    Note dr = (r_right-r_left)/(nr-1) here (not R[1]-R[0]); input not mutated.
+    """
+    p = np.array(psi, dtype=np.float64, copy=True)
+    s = np.asarray(source, dtype=np.float64)
+    nz, nr = p.shape
+    r_grid, _ = np.meshgrid(np.linspace(r_left, r_right, nr), np.linspace(z_bottom, z_top, nz))
+    dr = (r_right - r_left) / (nr - 1)
+    dz = (z_top - z_bottom) / (nz - 1)
+    return rb_sor_smooth(p, s, r_grid, dr, dz, omega, n_sweeps)
+
+
+# --------------------------------------------------------------------------
+# numerics helpers  (fusion_kernel_numerics.py)
+# --------------------------------------------------------------------------
+
+def sanitize(arr, cap=SANITIZE_CAP):
+    """fusion_kernel_numerics.py:19-24."""
+    out = np.nan_to_num(np.asarray(arr, dtype=np.float64), nan=0.0, posinf=cap, neginf=-cap)
+    if np.max(np.abs(out), initial=0.0) > cap:
+        out = np.clip(out, -cap, cap)
+    return out
+
+
+def stable_rms(arr) -> float:
+    """fusion_kernel_numerics.py:27-36 - max|x| * sqrt(mean((x/max|x|)^2))."""
+    v = sanitize(arr)
+    if v.size == 0:
+        return 0.0
+    m = float(np.max(np.abs(v), initial=0.0))
+    if m <= 0.0:
+        return 0.0
+    s = v / m
+    return float(m * np.sqrt(np.mean(s * s)))
+
+
+# --------------------------------------------------------------------------
+# elliptic integrals: Cephes ellpk / ellpe (what scipy.special wraps)
+# --------------------------------------------------------------------------
+
+_ELLPK_P = (1.37982864606273237150e-4, 2.28025724005875567385e-3, 7.97404013220415179367e-3,
+            9.85821379021226008714e-3, 6.87489687449949877925e-3, 6.18901033637687613229e-3,
+            8.79078273952743772254e-3, 1.49380448916805252718e-2, 3.08851465246711995998e-2,
+            9.65735902811690126535e-2, 1.38629436111989062502e0)
+_ELLPK_Q = (2.94078955048598507511e-5, 9.14184723865917226571e-4, 5.94058303753167793257e-3,
+            1.54850516649762399335e-2, 2.39089602715924892727e-2, 3.01204715227604046988e-2,
+            3.73774314173823228969e-2, 4.88280347570998239232e-2, 7.03124996963957469739e-2,
+            1.24999999999870820058e-1, 4.99999999999999999821e-1)
+_ELLPE_P = (1.53552577301013293365e-4, 2.50888492163602060990e-3, 8.68786816565889628429e-3,
+            1.07350949056076193403e-2, 7.77395492516787092951e-3, 7.58395289413514708519e-3,
+            1.15688436810574127319e-2, 2.18317996015557253103e-2, 5.68051945617860553470e-2,
+            4.43147180560990850618e-1, 1.00000000000000000299e0)
+_ELLPE_Q = (3.27954898576485872656e-5, 1.00962792679356715133e-3, 6.50609489976927491433e-3,
+            1.68862163993311317300e-2, 2.61769742454493659583e-2, 3.34833904888224918614e-2,
+            4.27180926518931511717e-2, 5.85936634471101055642e-2, 9.37499997197644278445e-2,
+            2.49999999999888314361e-1)
+
+
+def _horner(coeffs, x):
+    acc = np.full_like(x, coeffs[0])
+    for c in coeffs[1:]:
+        acc = acc * x + c
+    return acc
+
+
+def cephes_ellipk(m):
+    """K(m) for 0 <= m < 1: Cephes ellpk(1-m) = P(x) - log(x) Q(x), x = 1-m.
+
+    scipy.special.ellipk is this routine (called at fusion_kernel.py:242,
+    fusion_kernel_free_boundary.py:51,76); coefficients are the published
+    Cephes tables (also quoted at jax_equilibrium_solver.py:53-84).
+    """
+    x = 1.0 - np.asarray(m, dtype=np.float64)
+    return _horner(_ELLPK_P, x) - np.log(x) * _horner(_ELLPK_Q, x)
+
+
+def cephes_ellipe(m):
+    """E(m) for 0 <= m < 1: Cephes ellpe: P(x) - log(x) * (x Q(x)), x = 1-m."""
+    x = 1.0 - np.asarray(m, dtype=np.float64)
+    return _horner(_ELLPE_P, x) - np.log(x) * (x * _horner(_ELLPE_Q, x))
+
+
+def _ellip(m):
+    """K, E the way the reference gets them (scipy) with a Cephes fallback."""
+    try:
+        from scipy.special import ellipe, ellipk
+
+        return ellipk(m), ellipe(m)
+    except Exception:  # pragma: no cover - scipy is in the image
+        return cephes_ellipk(m), cephes_ellipe(m)
+
+
+# --------------------------------------------------------------------------
+# Green's functions
+# --------------------------------------------------------------------------
+
+def vacuum_field(R, Z, coils, mu0):
+    """fusion_kernel.py:218-251 - coil flux on the grid, config-units mu0, no self mask.
+
+    ``coils`` is a sequence of (r, z, current).
+    """
+    RR, ZZ = np.meshgrid(R, Z)
+    out = np.zeros((len(Z), len(R)))
+    for rc, zc, cur in coils:
+        dzz = ZZ - zc
+        k2 = (4.0 * RR * rc) / ((RR + rc) ** 2 + dzz ** 2)
+        k2 = np.clip(k2, 1e-12, 1.0 - 1e-12)
+        K, E = _ellip(k2)
+        pref = (mu0 * cur) / (2.0 * np.pi)
+        out += pref * np.sqrt(RR * rc) * (((2.0 - k2) * K - 2.0 * E) / np.sqrt(k2))
+    return out
+
+
+def green_vectorised(r_src, z_src, r_obs, z_obs):
+    """fusion_kernel_free_boundary.py:58-80 - SI Green's function, self point -> 0."""
+    r_obs = np.asarray(r_obs, dtype=np.float64)
+    z_obs = np.asarray(z_obs, dtype=np.float64)
+    self_mask = (r_obs - r_src) ** 2 + (z_obs - z_src) ** 2 < 1e-24
+    denom = (r_obs + r_src) ** 2 + (z_obs - z_src) ** 2
+    k2 = np.where(denom > 1e-30, 4.0 * r_obs * r_src / np.maximum(denom, 1e-30), 0.0)
+    k2 = np.clip(k2, 1e-12, 1.0 - 1e-12)
+    k = np.sqrt(k2)
+    K, E = _ellip(k2)
+    pref = MU0_SI / (2.0 * np.pi) * np.sqrt(r_obs * r_src)
+    return np.where(self_mask, 0.0, pref * ((2.0 - k2) * K - 2.0 * E) / k)
+
+
+def external_flux(R, Z, positions, currents, turns):
+    """fusion_kernel_free_boundary.py:83-93 - sum_c I_c*turns_c*G_c on the grid."""
+    RR, ZZ = np.meshgrid(R, Z)
+    out = np.zeros((len(Z), len(R)))
+    for i, ((rc, zc), cur) in enumerate(zip(positions, currents)):
+        t = turns[i] if i < len(turns) else 1
+        out += (cur * t) * green_vectorised(rc, zc, RR, ZZ)
+    return out
+
+
+def mutual_matrix(positions, turns, obs_points):
+    """fusion_kernel_free_boundary.py:137-153 - M[coil, point] = turns*G."""
+    obs = np.asarray(obs_points, dtype=np.float64)
+    M = np.zeros((len(positions), obs.shape[0]))
+    for k, (rc, zc) in enumerate(positions):
+        t = turns[k] if k < len(turns) else 1
+        M[k, :] = t * green_vectorised(rc, zc, obs[:, 0], obs[:, 1])
+    return M
+
+
+def wall_indices(nz, nr):
+    """jax_free_boundary_predictive.py:166-180 - flat wall-ring / interior indices (C order)."""
+    mask = np.zeros((nz, nr), bool)
+    mask[0, :] = mask[-1, :] = True
+    mask[:, 0] = mask[:, -1] = True
+    flat = mask.reshape(-1)
+    return np.where(flat)[0], np.where(~flat)[0]
+
+
+def greens_psi_si(R, Z, rc, zc, current=1.0, mu0=MU0_SI):
+    """jax_free_boundary_gs.py:70-86 - lane-C Green's function.
+
+    R_safe = max(R,1e-6); k2 clipped to [1e-9, 0.999999]; Cephes K/E;
+    ((2/k - k) K - (2/k) E); non-finite -> 0.  PARITY UNPINNED by a reference run.
+    """
+    R = np.maximum(np.asarray(R, dtype=np.float64), 1e-6)
+    Z = np.asarray(Z, dtype=np.float64)
+    denom = (R + rc) ** 2 + (Z - zc) ** 2
+    k2 = np.clip(4.0 * R * rc / np.maximum(denom, 1e-30), 1e-9, 0.999999)
+    k = np.sqrt(k2)
+    K, E = cephes_ellipk(k2), cephes_ellipe(k2)
+    psi = (mu0 * current / (2.0 * np.pi)) * np.sqrt(R * rc) * ((2.0 / k - k) * K - (2.0 / k) * E)
+    return np.where(np.isfinite(psi), psi, 0.0)
+
+
+def wall_response_matrix(R, Z, mu0=MU0_SI):
+    """jax_free_boundary_predictive.py:183-211 - M[wall b, interior s] = G_SI(b <- s)."""
+    nz, nr = len(Z), len(R)
+    RR, ZZ = np.meshgrid(R, Z)
+    b_idx, s_idx = wall_indices(nz, nr)
+    rw, zw = RR.reshape(-1)[b_idx], ZZ.reshape(-1)[b_idx]
+    rs, zs = RR.reshape(-1)[s_idx], ZZ.reshape(-1)[s_idx]
+    M = np.empty((b_idx.size, s_idx.size))
+    for j in range(s_idx.size):
+        M[:, j] = greens_psi_si(rw, zw, rs[j], zs[j], 1.0, mu0)
+    return M, b_idx, s_idx
+
+
+def plasma_wall_flux(M, s_idx, j_phi, dA):
+    """jax_free_boundary_predictive.py:498 - psi_wall = M @ (J[interior]*dA)."""
+    return M @ (np.asarray(j_phi).reshape(-1)[s_idx] * dA)
+
+
+# --------------------------------------------------------------------------
+# Picard pieces  (fusion_kernel.py, fusion_kernel_iterative_solver.py)
+# --------------------------------------------------------------------------
+
+def jacobi_step(psi, source, r_grid, dr, dz):
+    """fusion_kernel_iterative_solver.py:54-95 - out-of-place toroidal Jacobi, clipped."""
+    psi = sanitize(psi)
+    source = sanitize(source)
+    new = psi.copy()
+    a_e, a_w, a_ns, a_c = _stencil_coeffs(r_grid, dr, dz)
+    upd = (
+        a_e * psi[1:-1, 2:] + a_w * psi[1:-1, 0:-2] + a_ns * psi[0:-2, 1:-1] + a_ns * psi[2:, 1:-1]
+        - source[1:-1, 1:-1]
+    ) / a_c
+    new[1:-1, 1:-1] = np.clip(upd, -SANITIZE_CAP, SANITIZE_CAP)
+    return new
+
+
+def sor_step(psi, source, r_grid, dr, dz, omega=1.6):
+    """fusion_kernel_iterative_solver.py:97-161 - one clipped RB-SOR sweep on a sanitised copy."""
+    return rb_sor_smooth(sanitize(psi).copy(), sanitize(source), r_grid, dr, dz, omega, 1, clip=True)
+
+
+def find_axis(psi):
+    """fusion_kernel.py:342-355 - first global maximum (wall included), |psi|<1e-6 -> 1e-6."""
+    iz, ir = np.unravel_index(int(np.argmax(psi)), psi.shape)
+    v = float(psi[iz, ir])
+    if abs(v) < 1e-6:
+        v = 1e-6
+    return int(iz), int(ir), v
+
+
+def find_x_point(psi, R, Z, dr, dz, z_min, *, saddle=False):
+    """fusion_kernel.py:255-340 - min |grad psi| below 0.5*Z_min, optional saddle filter."""
+    raw = np.asarray(psi, dtype=np.float64)
+    fin = np.isfinite(raw)
+    if not fin.any():
+        return (0.0, 0.0), 0.0
+    safe = np.nan_to_num(raw, nan=0.0, posinf=1e300, neginf=-1e300)
+    gz, gr = np.gradient(safe, dz, dr)
+    b = np.hypot(gr, gz)
+    _, ZZ = np.meshgrid(R, Z)
+    div = (z_min * 0.5) > ZZ
+    if div.any():
+        mb = np.where(div, b, np.inf)
+        nfin = int(np.isfinite(mb).sum())
+        if nfin > 0:
+            def at(iz, ir):
+                v = float(raw[iz, ir])
+                if not np.isfinite(v):
+                    v = float(safe[iz, ir])
+                return (float(R[ir]), float(Z[iz])), v
+
+            if saddle:
+                ncand = min(16, nfin)
+                cand = np.argpartition(mb.ravel(), ncand - 1)[:ncand]
+                nz, nr = raw.shape
+                hits = []
+                for idx in cand:
+                    iz, ir = np.unravel_index(int(idx), raw.shape)
+                    if iz <= 0 or iz >= nz - 1 or ir <= 0 or ir >= nr - 1:
+                        continue
+                    d2r = (safe[iz, ir + 1] - 2.0 * safe[iz, ir] + safe[iz, ir - 1]) / (dr ** 2)
+                    d2z = (safe[iz + 1, ir] - 2.0 * safe[iz, ir] + safe[iz - 1, ir]) / (dz ** 2)
+                    drz = (safe[iz + 1, ir + 1] - safe[iz + 1, ir - 1] - safe[iz - 1, ir + 1]
+                           + safe[iz - 1, ir - 1]) / (4.0 * dr * dz)
+                    det = float(d2r * d2z - drz * drz)
+                    if np.isfinite(det) and det < 0.0:
+                        hits.append((float(mb[iz, ir]), int(iz), int(ir)))
+                if hits:
+                    _, iz, ir = min(hits, key=lambda t: t[0])
+                    return at(iz, ir)
+            iz, ir = np.unravel_index(int(np.argmin(mb)), raw.shape)
+            return at(iz, ir)
+    return (0.0, 0.0), float(np.min(raw[fin]))
+
+
+def mtanh_profile(psi_n, p):
+    """fusion_kernel.py:359-390 - pedestal + core, zero outside 0 <= psi_n < 1."""
+    out = np.zeros_like(psi_n)
+    m = (psi_n >= 0) & (psi_n < 1.0)
+    x = psi_n[m]
+    y = np.clip((p["ped_top"] - x) / p["ped_width"], -20, 20)
+    ped = 0.5 * p["ped_height"] * (1.0 + np.tanh(y))
+    core = np.where(x < p["ped_top"], np.maximum(0.0, 1.0 - (x / p["ped_top"]) ** 2), 0.0)
+    out[m] = ped + p["core_alpha"] * core
+    return out
+
+
+DEFAULT_PED = {"ped_top": 0.92, "ped_width": 0.05, "ped_height": 1.0, "core_alpha": 0.3}
+
+
+def plasma_source(psi, RR, dr, dz, psi_axis, psi_bnd, mu0, ip_target, *, hmode=False,
+                  ped_p=None, ped_ff=None):
+    """fusion_kernel.py:394-444 - J_phi from psi_N profiles, renormalised to Ip."""
+    denom = psi_bnd - psi_axis
+    if abs(denom) < 1e-9:
+        denom = 1e-9
+    pn = (psi - psi_axis) / denom
+    mask = (pn >= 0) & (pn < 1.0)
+    if hmode:
+        p_prof = mtanh_profile(pn, ped_p or DEFAULT_PED)
+        ff_prof = mtanh_profile(pn, ped_ff or DEFAULT_PED)
+    else:
+        p_prof = np.zeros_like(psi)
+        p_prof[mask] = 1.0 - pn[mask]
+        ff_prof = p_prof.copy()
+    j_p = RR * p_prof
+    j_f = (1.0 / (mu0 * RR)) * ff_prof
+    j_raw = 0.5 * j_p + (1 - 0.5) * j_f
+    i_cur = float(np.sum(j_raw)) * dr * dz
+    if abs(i_cur) > 1e-9:
+        return j_raw * (ip_target / i_cur)
+    return np.zeros_like(psi)
+
+
+def gs_residual_rms(psi, source, r_grid, dr, dz) -> float:
+    """fusion_kernel_solver_runtime.py:45-51 - stable RMS of the interior residual."""
+    r = gs_residual(psi, source, r_grid, dr, dz)[1:-1, 1:-1]
+    return stable_rms(r) if r.size else 0.0
+
+
+class PicardProblem:
+    """Grid + physics of one equilibrium, built from a reference-style config dict.
+
+    Mirrors FusionKernel.initialize_grid (fusion_kernel.py:158-200).
+    """
+
+    def __init__(self, cfg: dict[str, Any]):
+        self.cfg = cfg
+        d = cfg["dimensions"]
+        self.NR, self.NZ = int(cfg["grid_resolution"][0]), int(cfg["grid_resolution"][1])
+        self.R = np.linspace(d["R_min"], d["R_max"], self.NR)
+        self.Z = np.linspace(d["Z_min"], d["Z_max"], self.NZ)
+        self.dR = float(self.R[1] - self.R[0])
+        self.dZ = float(self.Z[1] - self.Z[0])
+        self.RR, self.ZZ = np.meshgrid(self.R, self.Z)
+        self.Psi = np.zeros((self.NZ, self.NR))
+        self.J_phi = np.zeros((self.NZ, self.NR))
+        self.hmode = False
+        self.ped_p = dict(DEFAULT_PED)
+        self.ped_ff = dict(DEFAULT_PED)
+        prof = cfg.get("physics", {}).get("profiles")
+        if prof:
+            self.hmode = prof.get("mode", "l-mode") in ("h-mode", "H-mode", "hmode")
+            self.ped_p.update(prof.get("p_prime", {}))
+            self.ped_ff.update(prof.get("ff_prime", {}))
+
+    def coils(self):
+        return [(c["r"], c["z"], c["current"]) for c in self.cfg["coils"]]
+
+
+def picard_solve(prob: PicardProblem, *, preserve_initial_state=False, boundary_flux=None,
+                 trace=None) -> dict[str, Any]:
+    """fusion_kernel_newton_solver.py:390-615 (methods multigrid/sor/jacobi; no anderson/newton).
+
+    ``trace`` (a list) receives per-iteration dicts of intermediates for tests.
+    """
+    t0 = time.time()
+    cfg = prob.cfg
+    sol = cfg["solver"]
+    method = sol.get("solver_method", "multigrid")
+    if method not in ("multigrid", "sor", "jacobi"):
+        raise ValueError(f"oracle covers multigrid/sor/jacobi, not {method!r}")
+    ip = cfg["physics"]["plasma_current_target"]
+    mu0 = cfg["physics"]["vacuum_permeability"]
+    if abs(ip) < 1e-12 and not preserve_initial_state:
+        prob.Psi = vacuum_field(prob.R, prob.Z, prob.coils(), cfg["physics"].get("vacuum_permeability", 1.0))
+        prob.J_phi = np.zeros_like(prob.Psi)
+        return {"psi": prob.Psi, "converged": True, "iterations": 0, "residual": 0.0,
+                "residual_history": [], "gs_residual": 0.0, "gs_residual_best": 0.0,
+                "gs_residual_history": [], "wall_time_s": time.time() - t0, "solver_method": method}
+
+    # _prepare_initial_flux  (fusion_kernel_iterative_solver.py:412-451)
+    if boundary_flux is not None:
+        bc = np.asarray(boundary_flux, dtype=np.float64)
+        if bc.shape != prob.Psi.shape:
+            raise ValueError("boundary_flux shape must match Psi shape")
+        bc = bc.copy()
+    elif preserve_initial_state:
+        bc = prob.Psi.copy()
+    else:
+        bc = vacuum_field(prob.R, prob.Z, prob.coils(), cfg["physics"].get("vacuum_permeability", 1.0))
+    if preserve_initial_state:
+        copy_wall(prob.Psi, bc)
+    else:
+        prob.Psi = bc.copy()
+
+    max_iter = sol["max_iterations"]
+    tol = sol["convergence_threshold"]
+    alpha = sol.get("relaxation_factor", 0.1)
+    omega = sol.get("sor_omega", 1.6)
+    fail = bool(sol.get("fail_on_diverge", False))
+    need_gs = bool(sol.get("require_gs_residual", False))
+    gs_tol = float(sol.get("gs_residual_threshold", tol))
+    if need_gs and gs_tol <= 0.0:
+        raise ValueError("solver.gs_residual_threshold must be > 0")
+    saddle = bool(sol.get("xpoint_use_saddle_detection", False))
+
+    best = prob.Psi.copy()
+    diff_best = 1e9
+    hist, gs_hist = [], []
+    gs_best = float("inf")
+    converged = False
+    last_src = None
+    xp = (0.0, 0.0)
+
+    # _seed_plasma  (fusion_kernel_iterative_solver.py:384-410)
+    if abs(ip) < 1e-12:
+        prob.J_phi = np.zeros_like(prob.Psi)
+    else:
+        rc = (cfg["dimensions"]["R_min"] + cfg["dimensions"]["R_max"]) / 2.0
+        prob.J_phi = np.exp(-((prob.RR - rc) ** 2 + prob.ZZ ** 2) / 2.0)
+        i_seed = float(np.sum(prob.J_phi)) * prob.dR * prob.dZ
+        if i_seed > 0:
+            prob.J_phi *= ip / i_seed
+        s0 = -mu0 * prob.RR * prob.J_phi
+        for _ in range(50):
+            prob.Psi = jacobi_step(prob.Psi, s0, prob.RR, prob.dR, prob.dZ)
+
+    k_last = 0
+    for k in range(max_iter):
+        k_last = k
+        _, _, p_ax = find_axis(prob.Psi)
+        xp, p_b = find_x_point(prob.Psi, prob.R, prob.Z, prob.dR, prob.dZ,
+                               cfg["dimensions"]["Z_min"], saddle=saddle)
+        if abs(p_ax - p_b) < 0.1:
+            p_b = p_ax * 0.1
+        prob.J_phi = plasma_source(prob.Psi, prob.RR, prob.dR, prob.dZ, p_ax, p_b, mu0, ip,
+                                   hmode=prob.hmode, ped_p=prob.ped_p, ped_ff=prob.ped_ff)
+        src = -mu0 * prob.RR * prob.J_phi
+        last_src = src
+        if method == "jacobi":
+            new = jacobi_step(prob.Psi, src, prob.RR, prob.dR, prob.dZ)
+        elif method == "multigrid":
+            new = vcycle(prob.Psi.copy(), src, prob.RR, prob.dR, prob.dZ, omega=omega)
+        else:
+            new = sor_step(prob.Psi, src, prob.RR, prob.dR, prob.dZ, omega=omega)
+        copy_wall(new, bc)
+        if np.isnan(new).any() or np.isinf(new).any():
+            prob.Psi = best
+            if fail:
+                raise RuntimeError(f"Equilibrium solver diverged at iter={k}")
+            break
+        diff = float(np.mean(np.abs(new - prob.Psi)))
+        hist.append(diff)
+        prob.Psi = (1.0 - alpha) * prob.Psi + alpha * new
+        gsr = gs_residual_rms(prob.Psi, src, prob.RR, prob.dR, prob.dZ)
+        gs_hist.append(gsr)
+        gs_best = min(gs_best, gsr)
+        if trace is not None:
+            trace.append({"psi_axis": p_ax, "psi_boundary": p_b, "x_point": xp, "diff": diff,
+                          "gs": gsr})
+        if diff < diff_best:
+            diff_best = diff
+            best = prob.Psi.copy()
+        if diff < tol and ((not need_gs) or gsr < gs_tol):
+            converged = True
+            break
+
+    if last_src is None:
+        gs_final = gs_best_out = float("inf")
+    elif gs_hist:
+        gs_final, gs_best_out = gs_hist[-1], gs_best
+    else:
+        gs_final = gs_best_out = gs_residual_rms(prob.Psi, last_src, prob.RR, prob.dR, prob.dZ)
+    return {"psi": prob.Psi, "converged": converged, "iterations": k_last + 1,
+            "residual": diff_best, "residual_history": hist, "gs_residual": gs_final,
+            "gs_residual_best": gs_best_out, "gs_residual_history": gs_hist,
+            "wall_time_s": time.time() - t0, "solver_method": method, "x_point": xp}
+
+
+def b_field(psi, RR, dr, dz):
+    """fusion_kernel.py:450-456 - B_R = -(1/R) dpsi/dZ, B_Z = (1/R) dpsi/dR."""
+    gz, gr = np.gradient(psi, dz, dr)
+    rs = np.maximum(RR, 1e-6)
+    return -(1.0 / rs) * gz, (1.0 / rs) * gr
+
+
+def free_boundary_solve(prob: PicardProblem, positions, currents, turns, *, max_outer_iter=20,
+                        tol=1e-4) -> dict[str, Any]:
+    """fusion_kernel_free_boundary.py:623-739 without shape optimisation.
+
+    Outer loop: coil flux on the wall -> warm-started Picard -> max|dPsi| < tol.
+    """
+    if max_outer_iter < 1:
+        raise ValueError("max_outer_iter must be >= 1.")
+    if not np.isfinite(tol) or tol < 0.0:
+        raise ValueError("tol must be finite and >= 0.")
+    psi_ext = external_flux(prob.R, prob.Z, positions, currents, turns)
+    diff = float("inf")
+    outer = 0
+    inner = []
+    for outer in range(max_outer_iter):
+        copy_wall(prob.Psi, psi_ext)
+        old = prob.Psi.copy()
+        res = picard_solve(prob, preserve_initial_state=True, boundary_flux=psi_ext)
+        inner.append(res["iterations"])
+        diff = float(np.max(np.abs(prob.Psi - old)))
+        if diff < tol:
+            break
+    return {"outer_iterations": outer + 1, "final_diff": diff,
+            "coil_currents": np.asarray(currents, dtype=np.float64).copy(),
+            "inner_iterations": inner, "psi": prob.Psi}
+
+
+# --------------------------------------------------------------------------
+# the reference's C ABI arithmetic (src/scpn_fusion/hpc/solver.cpp)
+# --------------------------------------------------------------------------
+
+def hpc_run_step(psi, j_phi, r_min, r_max, z_min, z_max, iterations, *, omega=1.8, wall=0.0):
+    """solver.cpp:96-188,243-268 - FastSolver RB-SOR (operand order differs from NumPy's).
+
+    p_gs = (src + c_z*(up+down) + c_r+*right + c_r-*left)/center with
+    src = -1.0*R*j, R = r_min + r*dr, dr = (r_max-r_min)/(nr-1); wall = constant.
+    Returns (psi, max|delta| of the last sweep).
+    """
+    nz, nr = psi.shape
+    dr = (r_max - r_min) / (nr - 1)
+    dz = (z_max - z_min) / (nz - 1)
+    Rrow = r_min + np.arange(nr) * dr
+    R = np.broadcast_to(Rrow, (nz, nr))
+    src = -1.0 * R * j_phi
+    c_p = 1.0 / (dr * dr) - 1.0 / (2.0 * R * dr)
+    c_m = 1.0 / (dr * dr) + 1.0 / (2.0 * R * dr)
+    c_z = 1.0 / (dz * dz)
+    cen = 2.0 / (dr * dr) + 2.0 / (dz * dz)
+    last = 0.0
+    for _ in range(max(int(iterations), 1)):
+        psi[0, :] = psi[-1, :] = wall
+        psi[:, 0] = psi[:, -1] = wall
+        last = 0.0
+        for parity in (0, 1):
+            for zs, rs in _colour_slices(nz, nr, parity):
+                up = psi[zs.start + 1 : nz : 2, rs]
+                down = psi[zs.start - 1 : nz - 2 : 2, rs]
+                right = psi[zs, rs.start + 1 : nr : 2]
+                left = psi[zs, rs.start - 1 : nr - 2 : 2]
+                gs = (src[zs, rs] + c_z * (up + down) + c_p[zs, rs] * right + c_m[zs, rs] * left) / cen
+                old = psi[zs, rs].copy()
+                new = (1.0 - omega) * old + omega * gs
+                psi[zs, rs] = new
+                if new.size:
+                    last = max(last, float(np.max(np.abs(new - old))))
+    return psi, last

@@ -1,0 +1,304 @@
+"""Generate the committed golden fixtures by running the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+Every array written here is the output of a reference function called through
+the reference's own API (``oracle/ref_shim.py`` only patches the numpy>=2 /
+matplotlib import problems).  The tests never read
+/root/reference; they read these .npz/.json files.
+"""
+from __future__ import annotations
+
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+import ref_shim  # noqa: E402
+
+ref_shim.install()
+
+from scpn_fusion.core import multigrid_solve as ref_mg  # noqa: E402
+from scpn_fusion.core import _multi_compat_providers as ref_prov  # noqa: E402
+from scpn_fusion.core.fusion_kernel import FusionKernel  # noqa: E402
+from scpn_fusion.core import fusion_kernel_free_boundary as ref_fb  # noqa: E402
+
+REF = ref_shim.REFERENCE_ROOT
+
+
+def _save(name, **arrays):
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **arrays)
+    print(f"wrote {name}.npz  ({os.path.getsize(path) / 1024:.1f} KiB)")
+
+
+def _kernel(cfg):
+    fd, p = tempfile.mkstemp(suffix=".json")
+    with os.fdopen(fd, "w") as f:
+        json.dump(cfg, f)
+    k = FusionKernel(p)
+    os.unlink(p)
+    return k
+
+
+def _cfg(name, n=None, **solver):
+    cfg = json.load(open(os.path.join(REF, "validation", name)))
+    cfg.pop("_reference", None)
+    if n is not None:
+        cfg["grid_resolution"] = [n[0], n[1]] if isinstance(n, (tuple, list)) else [n, n]
+    cfg["solver"].update(solver)
+    return cfg
+
+
+# -- 1. element-wise multigrid operators on random fields, several shapes ------
+
+def gen_ops():
+    out = {}
+    shapes = [(33, 33), (21, 37), (32, 32), (20, 36), (9, 9), (5, 5), (6, 7), (17, 9)]
+    out["shapes"] = np.array(shapes)
+    for i, (nz, nr) in enumerate(shapes):
+        rng = np.random.default_rng(1000 + i)
+        psi = rng.normal(size=(nz, nr))
+        src = rng.normal(size=(nz, nr))
+        r_axis = np.linspace(1.5, 4.25, nr)
+        z_axis = np.linspace(-1.0, 2.0, nz)
+        r_grid, _ = np.meshgrid(r_axis, z_axis)
+        dr = float(r_axis[1] - r_axis[0])
+        dz = float(z_axis[1] - z_axis[0])
+        t = f"s{i}_"
+        out[t + "psi"], out[t + "src"], out[t + "r_grid"] = psi, src, r_grid
+        out[t + "drdz"] = np.array([dr, dz])
+        out[t + "smooth_w13_2"] = ref_mg.mg_smooth(psi.copy(), src, r_grid, dr, dz, 1.3, 2)
+        out[t + "smooth_w10_1"] = ref_mg.mg_smooth(psi.copy(), src, r_grid, dr, dz, 1.0, 1)
+        out[t + "residual"] = ref_mg.mg_residual(psi, src, r_grid, dr, dz)
+        out[t + "restrict"] = ref_mg.restrict_full_weight(psi)
+        out[t + "restrict_r"] = ref_mg.restrict_full_weight(r_grid)
+        coarse = rng.normal(size=((nz + 1) // 2, (nr + 1) // 2))
+        out[t + "coarse"] = coarse
+        out[t + "prolong"] = ref_mg.prolongate_bilinear(coarse, nz, nr)
+        out[t + "vcycle_w10"] = ref_mg.multigrid_vcycle(psi.copy(), src, r_grid, dr, dz, omega=1.0)
+        out[t + "vcycle_w16"] = ref_mg.multigrid_vcycle(psi.copy(), src, r_grid, dr, dz, omega=1.6)
+        out[t + "linf"] = np.array(ref_mg.residual_linf(psi, src, r_grid, dr, dz))
+    _save("mg_ops", **out)
+
+
+# -- 2. multigrid_solve known answers ------------------------------------------
+
+def gen_mg_solve():
+    out = {}
+    # the pinned 33^2 checksum case, benchmarks/bench_dispatcher_kernel_tiers.py:69-76
+    nr = nz = 33
+    r_min, r_max, z_min, z_max = 1.2, 2.2, -0.5, 0.5
+    rr, zz = np.meshgrid(np.linspace(r_min, r_max, nr), np.linspace(z_min, z_max, nz))
+    source = np.asarray(-rr * np.exp(-((rr - 1.7) ** 2 + zz ** 2) / 0.05), dtype=np.float64)
+    psi, res, n, conv = ref_mg.multigrid_solve(source, np.zeros((nz, nr)), r_min, r_max, z_min,
+                                               z_max, nr, nz, tol=1e-6, max_cycles=120)
+    out["c33_source"], out["c33_psi"] = source, psi
+    out["c33_meta"] = np.array([res, n, float(conv), float(np.sum(psi)) + res + n + float(conv)])
+    # Gaussian source with a non-zero Dirichlet ring, rectangular and even grids
+    for tag, (nz, nr) in {"g65": (65, 65), "g40x72": (40, 72), "g49x97": (49, 97)}.items():
+        rng = np.random.default_rng(7)
+        r_min, r_max, z_min, z_max = 4.0, 8.0, -4.0, 4.0
+        rr, zz = np.meshgrid(np.linspace(r_min, r_max, nr), np.linspace(z_min, z_max, nz))
+        source = -np.exp(-((rr - 6.0) ** 2 + zz ** 2) / 0.5)
+        bc = 0.01 * rng.normal(size=(nz, nr))
+        psi, res, n, conv = ref_mg.multigrid_solve(source, bc, r_min, r_max, z_min, z_max, nr, nz,
+                                                   tol=1e-8, max_cycles=60)
+        out[tag + "_source"], out[tag + "_bc"], out[tag + "_psi"] = source, bc, psi
+        out[tag + "_meta"] = np.array([res, n, float(conv)])
+    _save("mg_solve", **out)
+
+
+# -- 3. the bench_gpu_gs_solver smoother problem --------------------------------
+
+def gen_bench_smooth():
+    out = {}
+    for n, sweeps in ((65, 50), (129, 200)):
+        rng = np.random.default_rng(2026)
+        r_axis = np.linspace(4.0, 8.0, n)
+        z_axis = np.linspace(-4.0, 4.0, n)
+        r_grid, z_grid = np.meshgrid(r_axis, z_axis)
+        source = -np.exp(-((r_grid - 6.0) ** 2 + z_grid ** 2) / 0.5)
+        psi0 = rng.normal(0.0, 1e-3, size=(n, n))
+        psi0[0, :] = psi0[-1, :] = psi0[:, 0] = psi0[:, -1] = 0.0
+        sol = ref_prov._numpy_gs_rb_sor_smooth(psi0, source, 4.0, 8.0, -4.0, 4.0, omega=1.3,
+                                               n_sweeps=sweeps)
+        out[f"n{n}_out"] = sol
+        out[f"n{n}_sweeps"] = np.array(sweeps)
+    _save("bench_smooth", **out)
+
+
+# -- 4. Picard pieces on real iterates ------------------------------------------
+
+def gen_picard_pieces():
+    out = {}
+    cfg = _cfg("iter_validated_config.json", 65, max_iterations=40)
+    k = _kernel(cfg)
+    k.solve_equilibrium()
+    psi = k.Psi.copy()
+    out["psi"] = psi
+    out["RZ"] = np.stack([k.R, k.Z])
+    iz, ir, pax = k._find_magnetic_axis()
+    out["axis"] = np.array([iz, ir, pax])
+    (rx, zx), px = k.find_x_point(psi)
+    out["xpoint"] = np.array([rx, zx, px])
+    k.cfg["solver"]["xpoint_use_saddle_detection"] = True
+    (rx, zx), px = k.find_x_point(psi)
+    out["xpoint_saddle"] = np.array([rx, zx, px])
+    k.cfg["solver"]["xpoint_use_saddle_detection"] = False
+    pb = px if abs(pax - px) >= 0.1 else pax * 0.1
+    out["axis_bnd"] = np.array([pax, pb])
+    out["j_lmode"] = k.update_plasma_source_nonlinear(pax, pb).copy()
+    k.profile_mode = "h-mode"
+    k.ped_params_p.update({"ped_top": 0.9, "ped_width": 0.06, "ped_height": 1.1, "core_alpha": 0.25})
+    out["j_hmode"] = k.update_plasma_source_nonlinear(pax, pb).copy()
+    out["ped_p"] = np.array([0.9, 0.06, 1.1, 0.25])
+    out["ped_ff"] = np.array([0.92, 0.05, 1.0, 0.3])
+    k.profile_mode = "l-mode"
+    src = -1.0 * k.RR * out["j_lmode"]
+    out["jacobi"] = k._jacobi_step(psi, src)
+    out["sor16"] = k._sor_step(psi, src, omega=1.6)
+    out["gs_rms"] = np.array(k._compute_gs_residual_rms(src))
+    k.compute_b_field()
+    out["b_r"], out["b_z"] = k.B_R, k.B_Z
+    out["vacuum"] = k.calculate_vacuum_field()
+    coils = k.build_coilset_from_config()
+    coils.turns = [1, 2, 1, 3, 1, 1, 4]
+    out["ext_flux"] = ref_fb.compute_external_flux(k, coils)
+    pts = np.array([[5.0, 0.5], [6.5, -2.0], [3.9, 7.6], [8.0, 0.0]])
+    out["mutual_pts"] = pts
+    out["mutual"] = ref_fb.build_mutual_inductance_matrix(k, coils, pts)
+    out["turns"] = np.array(coils.turns)
+    _save("picard_pieces", **out)
+
+
+# -- 5. full solve_equilibrium runs ---------------------------------------------
+
+def _solve_case(out, tag, cfg, keep_psi=True):
+    k = _kernel(cfg)
+    r = k.solve_equilibrium()
+    (rx, zx), px = k.find_x_point(k.Psi)
+    iz, ir, pax = k._find_magnetic_axis()
+    if keep_psi:
+        out[tag + "_psi"] = r["psi"]
+        out[tag + "_jphi"] = k.J_phi
+    out[tag + "_hist"] = np.array(r["residual_history"])
+    out[tag + "_gshist"] = np.array(r["gs_residual_history"])
+    out[tag + "_meta"] = np.array([r["iterations"], float(r["converged"]), r["residual"],
+                                   r["gs_residual"], r["gs_residual_best"]])
+    out[tag + "_topo"] = np.array([k.R[ir], k.Z[iz], pax, rx, zx, px])
+    out[tag + "_cfg"] = np.array(json.dumps(cfg))
+    print(f"  {tag}: iters={r['iterations']} conv={r['converged']} t={r['wall_time_s']:.2f}s "
+          f"axis=({k.R[ir]:.3f},{k.Z[iz]:.3f}) x=({rx:.3f},{zx:.3f})")
+    return k
+
+
+def gen_solves():
+    out = {}
+    _solve_case(out, "iter65", _cfg("iter_config.json", 65))
+    _solve_case(out, "iter129", _cfg("iter_config.json", 129))
+    _solve_case(out, "iter64", _cfg("iter_config.json", 64))
+    _solve_case(out, "iter48x80", _cfg("iter_config.json", (48, 80)))
+    _solve_case(out, "iterval65", _cfg("iter_validated_config.json", 65))
+    _solve_case(out, "diiid65", _cfg("diiid_config.json", 65))
+    _solve_case(out, "diiid65s", _cfg("diiid_config.json", 65, xpoint_use_saddle_detection=True))
+    _solve_case(out, "iter65sor", _cfg("iter_config.json", 65, solver_method="sor", max_iterations=60))
+    _solve_case(out, "iter65jac", _cfg("iter_config.json", 65, solver_method="jacobi", max_iterations=60))
+    _solve_case(out, "iter65gs", _cfg("iter_config.json", 65, require_gs_residual=True,
+                                       gs_residual_threshold=5e-3, max_iterations=200))
+    # H-mode UQ samples, recipe of SURVEY.md 8d config 3 / tools/parallel_gen_iter.py:96-101
+    for ksample in range(3):
+        cfg = _cfg("iter_config.json", 65)
+        rng = np.random.default_rng(2026 + ksample)
+        for c in cfg["coils"]:
+            c["current"] = c["current"] * float(rng.uniform(0.85, 1.15))
+        cfg["physics"]["plasma_current_target"] *= float(rng.uniform(0.8, 1.2))
+        ped = {"ped_top": 0.92 * float(rng.uniform(0.97, 1.03)),
+               "ped_width": 0.05 * float(rng.uniform(0.9, 1.1)),
+               "ped_height": 1.0 * float(rng.uniform(0.9, 1.1)),
+               "core_alpha": 0.3 * float(rng.uniform(0.9, 1.1))}
+        cfg["physics"]["profiles"] = {"mode": "h-mode", "p_prime": ped, "ff_prime": dict(ped)}
+        _solve_case(out, f"uq65_{ksample}", cfg)
+    _save("solves", **out)
+
+
+def gen_solve_129_validated():
+    out = {}
+    _solve_case(out, "iterval129", _cfg("iter_validated_config.json", 129))
+    _save("solve_iterval129", **out)
+
+
+# -- 6. free boundary -------------------------------------------------------------
+
+def gen_free_boundary():
+    out = {}
+    cfg = _cfg("iter_validated_config.json", 33)
+    k = _kernel(cfg)
+    coils = k.build_coilset_from_config()
+    coils.currents = coils.currents * 1.0e6  # SI amperes so the SI-mu0 wall flux is O(1)
+    res = k.solve_free_boundary(coils, max_outer_iter=4, tol=1e-4)
+    out["psi"] = k.Psi
+    out["meta"] = np.array([res["outer_iterations"], res["final_diff"]])
+    out["currents"] = coils.currents
+    out["cfg"] = np.array(json.dumps(cfg))
+    print("  free boundary:", res["outer_iterations"], res["final_diff"])
+    _save("free_boundary", **out)
+
+
+# -- 7. the reference's compiled C++ solver (hpc/solver.cpp) ----------------------
+
+def gen_hpc():
+    so = os.path.join(ROOT, "oracle", "_ref", "libscpn_solver.so")
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "ref"])
+    lib = ctypes.CDLL(so)
+    lib.create_solver.restype = ctypes.c_void_p
+    lib.create_solver.argtypes = [ctypes.c_int, ctypes.c_int] + [ctypes.c_double] * 4
+    dp = ctypes.POINTER(ctypes.c_double)
+    lib.run_step.argtypes = [ctypes.c_void_p, dp, dp, ctypes.c_int, ctypes.c_int]
+    lib.run_step_converged.argtypes = [ctypes.c_void_p, dp, dp, ctypes.c_int, ctypes.c_int,
+                                       ctypes.c_double, ctypes.c_double, dp]
+    lib.run_step_converged.restype = ctypes.c_int
+    lib.set_boundary_dirichlet.argtypes = [ctypes.c_void_p, ctypes.c_double]
+    lib.destroy_solver.argtypes = [ctypes.c_void_p]
+    out = {}
+    nz, nr = 33, 41
+    rng = np.random.default_rng(5)
+    j = rng.normal(size=(nz, nr))
+    h = lib.create_solver(nr, nz, 2.0, 10.0, -4.0, 4.0)
+    psi = np.zeros((nz, nr))
+    lib.run_step(h, j.ctypes.data_as(dp), psi.ctypes.data_as(dp), nz * nr, 7)
+    out["j"], out["psi_7"] = j, psi.copy()
+    lib.run_step(h, j.ctypes.data_as(dp), psi.ctypes.data_as(dp), nz * nr, 5)  # warm: 12 total
+    out["psi_12"] = psi.copy()
+    lib.set_boundary_dirichlet(h, 0.25)
+    delta = ctypes.c_double(0.0)
+    n = lib.run_step_converged(h, j.ctypes.data_as(dp), psi.ctypes.data_as(dp), nz * nr, 400, 1.5,
+                               1e-9, ctypes.byref(delta))
+    out["psi_conv"] = psi.copy()
+    out["conv_meta"] = np.array([n, delta.value])
+    lib.destroy_solver(h)
+    _save("hpc_solver", **out)
+
+
+def gen_elliptic():
+    tab = json.load(open(os.path.join(REF, "scpn-fusion-rs", "tests", "reference", "reference_elliptic.json")))
+    m = np.array([float(x) for x in tab["K"].keys()])
+    _save("elliptic", m=m, K=np.array(list(tab["K"].values())), E=np.array(list(tab["E"].values())))
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["ops", "mg_solve", "bench_smooth", "picard_pieces", "solves",
+                             "solve_129_validated", "free_boundary", "hpc", "elliptic"]
+    for w in which:
+        print("==", w)
+        globals()["gen_" + w]()

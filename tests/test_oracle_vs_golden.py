@@ -1,0 +1,218 @@
+"""Pin the CPU oracle (oracle/gs_oracle.py) against outputs of the UNMODIFIED reference.
+
+The fixtures under tests/golden/ were produced by tests/golden/make_golden.py, which
+calls the reference's own functions.  Element-wise operators must be bit-identical;
+the full Picard solve is allowed 1e-13 (np.sum / np.mean are the same calls, so in
+practice it is bit-identical too).
+"""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+import gs_oracle as G
+from conftest import golden, golden_cfg, rel_l2
+
+
+def test_multigrid_operators_bit_exact():
+    z = golden("mg_ops")
+    for i, (nz, nr) in enumerate(z["shapes"]):
+        t = f"s{i}_"
+        psi, src, rg = z[t + "psi"], z[t + "src"], z[t + "r_grid"]
+        dr, dz = z[t + "drdz"]
+        np.testing.assert_array_equal(G.rb_sor_smooth(psi.copy(), src, rg, dr, dz, 1.3, 2), z[t + "smooth_w13_2"])
+        np.testing.assert_array_equal(G.rb_sor_smooth(psi.copy(), src, rg, dr, dz, 1.0, 1), z[t + "smooth_w10_1"])
+        np.testing.assert_array_equal(G.gs_residual(psi, src, rg, dr, dz), z[t + "residual"])
+        np.testing.assert_array_equal(G.restrict_full_weight(psi), z[t + "restrict"])
+        np.testing.assert_array_equal(G.restrict_full_weight(rg), z[t + "restrict_r"])
+        np.testing.assert_array_equal(G.prolong_bilinear(z[t + "coarse"], nz, nr), z[t + "prolong"])
+        np.testing.assert_array_equal(G.vcycle(psi.copy(), src, rg, dr, dz, omega=1.0), z[t + "vcycle_w10"])
+        np.testing.assert_array_equal(G.vcycle(psi.copy(), src, rg, dr, dz, omega=1.6), z[t + "vcycle_w16"])
+        assert G.residual_linf(psi, src, rg, dr, dz) == float(z[t + "linf"])
+
+
+def test_mg_solve_pinned_checksum():
+    """validation/reports/dispatcher_kernel_tiers_benchmark.json: output_checksum 22.46587229431361."""
+    z = golden("mg_solve")
+    psi, res, n, conv = G.mg_solve(z["c33_source"], np.zeros((33, 33)), 1.2, 2.2, -0.5, 0.5, 33, 33,
+                                   tol=1e-6, max_cycles=120)
+    np.testing.assert_array_equal(psi, z["c33_psi"])
+    assert (res, n, conv) == (z["c33_meta"][0], int(z["c33_meta"][1]), bool(z["c33_meta"][2]))
+    checksum = float(np.sum(psi)) + res + n + float(conv)
+    assert abs(checksum - 22.46587229431361) < 1e-12
+    assert n == 5
+
+
+@pytest.mark.parametrize("tag,shape", [("g65", (65, 65)), ("g40x72", (40, 72)), ("g49x97", (49, 97))])
+def test_mg_solve_cases(tag, shape):
+    z = golden("mg_solve")
+    nz, nr = shape
+    psi, res, n, conv = G.mg_solve(z[tag + "_source"], z[tag + "_bc"], 4.0, 8.0, -4.0, 4.0, nr, nz,
+                                   tol=1e-8, max_cycles=60)
+    np.testing.assert_array_equal(psi, z[tag + "_psi"])
+    assert (res, n, float(conv)) == tuple(z[tag + "_meta"])
+
+
+def test_mg_solve_input_validation():
+    s = np.zeros((9, 9))
+    with pytest.raises(ValueError):
+        G.mg_solve(s, np.zeros((9, 8)), 1, 2, 0, 1, 9, 9)
+    with pytest.raises(ValueError):
+        G.mg_solve(s, s, 1, 2, 0, 1, 9, 9, tol=0.0)
+    with pytest.raises(ValueError):
+        G.mg_solve(s, s, 1, 2, 0, 1, 9, 9, max_cycles=0)
+    for bad in (0.99, 2.0, float("nan")):
+        with pytest.raises(ValueError):
+            G.rb_sor_smooth(s.copy(), s, np.ones((9, 9)), 0.1, 0.1, bad, 1)
+
+
+def test_manufactured_fixed_point():
+    """tests/test_multigrid_solve.py:100-109 (reference): exact discrete solution stays fixed."""
+    nz = nr = 33
+    r = np.linspace(1.0, 2.0, nr)
+    zc = np.linspace(-0.5, 0.5, nz)
+    rr, zz = np.meshgrid(r, zc)
+    psi = 0.03125 * rr ** 4 - 0.125 * zz ** 2 + 0.05 * rr ** 2 * zz ** 2
+    dr, dz = float(r[1] - r[0]), float(zc[1] - zc[0])
+    src = np.zeros_like(psi)
+    src[1:-1, 1:-1] = G.gs_operator(psi, rr, dr, dz)[1:-1, 1:-1]
+    out, res, n, conv = G.mg_solve(src, psi, 1.0, 2.0, -0.5, 0.5, nr, nz, tol=1e-12)
+    assert conv and n == 0 and res < 1e-12
+
+
+def test_bench_smoother_problem():
+    z = golden("bench_smooth")
+    for n in (65, 129):
+        rng = np.random.default_rng(2026)
+        rg, zg = np.meshgrid(np.linspace(4.0, 8.0, n), np.linspace(-4.0, 4.0, n))
+        source = -np.exp(-((rg - 6.0) ** 2 + zg ** 2) / 0.5)
+        psi0 = rng.normal(0.0, 1e-3, size=(n, n))
+        psi0[0, :] = psi0[-1, :] = psi0[:, 0] = psi0[:, -1] = 0.0
+        keep = psi0.copy()
+        out = G.provider_rb_sor_smooth(psi0, source, 4.0, 8.0, -4.0, 4.0, omega=1.3,
+                                       n_sweeps=int(z[f"n{n}_sweeps"]))
+        np.testing.assert_array_equal(out, z[f"n{n}_out"])
+        np.testing.assert_array_equal(psi0, keep)  # input not mutated
+
+
+def _pieces():
+    z = golden("picard_pieces")
+    R, Z = z["RZ"]
+    return z, R, Z, float(R[1] - R[0]), float(Z[1] - Z[0])
+
+
+def test_topology_and_source():
+    z, R, Z, dr, dz = _pieces()
+    psi = z["psi"]
+    iz, ir, pax = G.find_axis(psi)
+    assert (iz, ir, pax) == (int(z["axis"][0]), int(z["axis"][1]), z["axis"][2])
+    (rx, zx), px = G.find_x_point(psi, R, Z, dr, dz, -6.0)
+    assert (rx, zx, px) == tuple(z["xpoint"])
+    (rx, zx), px = G.find_x_point(psi, R, Z, dr, dz, -6.0, saddle=True)
+    assert (rx, zx, px) == tuple(z["xpoint_saddle"])
+    RR, _ = np.meshgrid(R, Z)
+    pax, pb = z["axis_bnd"]
+    j = G.plasma_source(psi, RR, dr, dz, pax, pb, 1.0, 15.0)
+    np.testing.assert_array_equal(j, z["j_lmode"])
+    pp = dict(zip(("ped_top", "ped_width", "ped_height", "core_alpha"), z["ped_p"]))
+    pf = dict(zip(("ped_top", "ped_width", "ped_height", "core_alpha"), z["ped_ff"]))
+    jh = G.plasma_source(psi, RR, dr, dz, pax, pb, 1.0, 15.0, hmode=True, ped_p=pp, ped_ff=pf)
+    np.testing.assert_array_equal(jh, z["j_hmode"])
+    src = -1.0 * RR * z["j_lmode"]
+    np.testing.assert_array_equal(G.jacobi_step(psi, src, RR, dr, dz), z["jacobi"])
+    np.testing.assert_array_equal(G.sor_step(psi, src, RR, dr, dz, 1.6), z["sor16"])
+    # gs_rms golden was taken with kernel.Psi == psi at that point
+    assert G.gs_residual_rms(psi, src, RR, dr, dz) == float(z["gs_rms"])
+    br, bz = G.b_field(psi, RR, dr, dz)
+    np.testing.assert_array_equal(br, z["b_r"])
+    np.testing.assert_array_equal(bz, z["b_z"])
+
+
+def test_x_point_degenerate_inputs():
+    R = np.linspace(1, 2, 9)
+    Z = np.linspace(-1, 1, 9)
+    assert G.find_x_point(np.full((9, 9), np.nan), R, Z, 0.125, 0.25, -1.0) == ((0.0, 0.0), 0.0)
+    # no row below 0.5*z_min (z_min >= 0): fallback to min psi at (0,0)
+    Zp = np.linspace(0.0, 1.0, 9)
+    psi = np.arange(81.0).reshape(9, 9)
+    assert G.find_x_point(psi, R, Zp, 0.125, 0.125, 0.0) == ((0.0, 0.0), 0.0)
+
+
+def test_greens_functions():
+    import json
+    z, R, Z, dr, dz = _pieces()
+    coils = [(3.9, 7.6, 5.0), (8.2, 6.7, -1.0), (12.0, 2.7, 0.0), (12.6, -2.3, 0.0), (8.4, -6.7, -1.0),
+             (4.3, -7.6, 8.0), (1.7, 0.0, -5.0)]
+    np.testing.assert_array_equal(G.vacuum_field(R, Z, coils, 1.0), z["vacuum"])
+    pos = [(c[0], c[1]) for c in coils]
+    cur = [c[2] for c in coils]
+    turns = [int(t) for t in z["turns"]]
+    np.testing.assert_array_equal(G.external_flux(R, Z, pos, cur, turns), z["ext_flux"])
+    np.testing.assert_array_equal(G.mutual_matrix(pos, turns, z["mutual_pts"]), z["mutual"])
+
+
+def test_cephes_elliptic_vs_reference_table_and_scipy():
+    """scpn-fusion-rs/tests/reference/reference_elliptic.json (13 values of K, E)."""
+    from scipy.special import ellipe, ellipk
+
+    z = golden("elliptic")
+    np.testing.assert_allclose(G.cephes_ellipk(z["m"]), z["K"], rtol=3e-16, atol=0)
+    np.testing.assert_allclose(G.cephes_ellipe(z["m"]), z["E"], rtol=3e-16, atol=0)
+    m = np.concatenate([np.linspace(1e-12, 1 - 1e-12, 4001), 1 - np.logspace(-12, -1, 200)])
+    np.testing.assert_allclose(G.cephes_ellipk(m), ellipk(m), rtol=4e-16, atol=0)
+    np.testing.assert_allclose(G.cephes_ellipe(m), ellipe(m), rtol=4e-16, atol=0)
+
+
+SOLVE_TAGS = ["iter65", "iter64", "iter48x80", "diiid65", "diiid65s", "iter65sor", "iter65jac", "iter65gs",
+              "uq65_0", "uq65_1", "uq65_2"]
+
+
+@pytest.mark.parametrize("tag", SOLVE_TAGS)
+def test_picard_solve_matches_reference(tag):
+    z = golden("solves")
+    prob = G.PicardProblem(golden_cfg(z, tag))
+    r = G.picard_solve(prob)
+    meta = z[tag + "_meta"]
+    assert r["iterations"] == int(meta[0])
+    assert r["converged"] == bool(meta[1])
+    assert rel_l2(r["psi"], z[tag + "_psi"]) <= 1e-13
+    assert rel_l2(prob.J_phi, z[tag + "_jphi"]) <= 1e-12
+    np.testing.assert_allclose(r["residual_history"], z[tag + "_hist"], rtol=1e-9)
+    np.testing.assert_allclose(r["gs_residual_history"], z[tag + "_gshist"], rtol=1e-9)
+    assert abs(r["residual"] - meta[2]) <= 1e-12 * abs(meta[2])
+
+
+def test_picard_solve_iter129_and_validated65():
+    z = golden("solves")
+    for tag in ("iter129", "iterval65"):
+        prob = G.PicardProblem(golden_cfg(z, tag))
+        r = G.picard_solve(prob)
+        assert r["iterations"] == int(z[tag + "_meta"][0])
+        assert rel_l2(r["psi"], z[tag + "_psi"]) <= 1e-13
+        iz, ir, pax = G.find_axis(prob.Psi)
+        topo = z[tag + "_topo"]
+        assert (prob.R[ir], prob.Z[iz]) == (topo[0], topo[1])
+        assert r["x_point"] is not None
+
+
+def test_free_boundary_outer_loop():
+    import json
+    z = golden("free_boundary")
+    cfg = json.loads(str(z["cfg"]))
+    prob = G.PicardProblem(cfg)
+    pos = [(c["r"], c["z"]) for c in cfg["coils"]]
+    r = G.free_boundary_solve(prob, pos, z["currents"], [1] * len(pos), max_outer_iter=4, tol=1e-4)
+    assert r["outer_iterations"] == int(z["meta"][0])
+    assert rel_l2(r["psi"], z["psi"]) <= 1e-13
+    assert abs(r["final_diff"] - z["meta"][1]) <= 1e-12 * abs(z["meta"][1])
+
+
+def test_hpc_cpp_arithmetic():
+    """oracle.hpc_run_step vs the compiled reference solver.cpp (FMA contraction allowed there)."""
+    z = golden("hpc_solver")
+    j = z["j"]
+    psi = np.zeros_like(j)
+    psi, _ = G.hpc_run_step(psi, j, 2.0, 10.0, -4.0, 4.0, 7)
+    assert rel_l2(psi, z["psi_7"]) < 1e-13
+    psi, _ = G.hpc_run_step(psi, j, 2.0, 10.0, -4.0, 4.0, 5)
+    assert rel_l2(psi, z["psi_12"]) < 1e-13
