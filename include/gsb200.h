@@ -1,0 +1,219 @@
+/* gsb200.h - C ABI of libgsb200.so: the B200-native Grad-Shafranov hot path.
+ *
+ * Two groups of entry points (reference paths are relative to the reference root):
+ *
+ *  A. The reference's own native ABI, verbatim: the six symbols its ctypes bridge
+ *     binds (src/scpn_fusion/hpc/hpc_bridge.py:190-250) and its C++ solver exports
+ *     (src/scpn_fusion/hpc/solver.cpp:200-335).  HOST pointers, row-major [iz][ir]
+ *     float64, size == nz*nr.  libgsb200.so can be handed to the reference through
+ *     SCPN_SOLVER_LIB unchanged.
+ *
+ *  B. The device API (gsb_*): what the Python host mirror of the reference's
+ *     solver surface (scpn_fusion_core_b200/) calls.  All `*_dev` arguments are
+ *     DEVICE pointers (e.g. torch.Tensor.data_ptr()), dense C-order float64
+ *     [batch][nz][nr] unless stated; `stream` is a cudaStream_t passed as void*
+ *     (NULL = legacy default stream).  No exceptions cross the ABI: functions
+ *     return GSB_OK (0) or a negative GSB_E* code; gsb_last_error() gives the text.
+ *     Nothing here falls back to the CPU: without a CUDA device every call that
+ *     would compute returns GSB_ENODEV.
+ *
+ * Plain C types only; no torch / CUDA types in any signature.
+ */
+#ifndef GSB200_H
+#define GSB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSB_ABI_VERSION 1
+
+enum {
+  GSB_OK = 0,
+  GSB_EINVAL = -1,  /* bad argument (NULL pointer, shape, omega outside [1,2), ...) */
+  GSB_ENODEV = -2,  /* no usable CUDA device */
+  GSB_ECUDA = -3,   /* a CUDA runtime call failed; see gsb_last_error() */
+  GSB_ENOMEM = -4,
+  GSB_ESTATE = -5   /* call sequence error (e.g. Picard state not set) */
+};
+
+/* ------------------------------------------------------------------------- */
+/* A. reference native ABI (solver.cpp:200-335 / hpc_bridge.py:190-250)      */
+/* ------------------------------------------------------------------------- */
+
+/* solver.cpp:205 - NULL if nr<2 || nz<2 || rmin>=rmax || zmin>=zmax (or no GPU). */
+void *create_solver(int nr, int nz, double rmin, double rmax, double zmin, double zmax);
+/* solver.cpp:226 - constant Dirichlet wall value; NULL handle ignored. */
+void set_boundary_dirichlet(void *solver_ptr, double boundary_value);
+/* solver.cpp:243 - max(iterations,1) RB-SOR sweeps at omega=1.8 of
+ * source = -1.0*R*j; psi persists in the handle across calls (warm start). */
+void run_step(void *solver_ptr, const double *j_array, double *psi_array, int size, int iterations);
+/* solver.cpp:273 - sweeps until max|delta psi| <= tol; omega clamped to [0.1,1.99];
+ * returns sweeps done (>=1), 0 on invalid input. */
+int run_step_converged(void *solver_ptr, const double *j_array, double *psi_array, int size,
+                       int max_iterations, double omega, double tolerance, double *final_delta_out);
+/* solver.cpp:325,331 */
+void destroy_solver(void *solver_ptr);
+void delete_solver(void *solver_ptr);
+
+/* ------------------------------------------------------------------------- */
+/* B. device API                                                             */
+/* ------------------------------------------------------------------------- */
+
+typedef struct gsb_ctx gsb_ctx;
+
+int gsb_abi_version(void);
+const char *gsb_last_error(void);
+/* Number of visible CUDA devices (0 without a GPU; never fails). */
+int gsb_device_count(void);
+/* Count of kernels launched by this library in this process (bench.py's gpu_launches). */
+long long gsb_launch_count(void);
+
+/* Host-only planning helper (works without a GPU): level sizes of the V-cycle
+ * the reference would run on (nz,nr) with `min_grid` (multigrid_solve.py:292,
+ * coarse size (n+1)//2).  Writes up to `cap` (nz,nr) pairs, returns the number of
+ * levels including the base level. */
+int gsb_plan_levels(int nz, int nr, int min_grid, int *nz_out, int *nr_out, int cap);
+/* Host-only: per-level interior-row R values and stencil columns exactly as the
+ * reference derives them (restrict_full_weight of r_grid, multigrid_solve.py:307;
+ * a_e/a_w, :186-187).  out arrays hold nr_level doubles (walls = 0). */
+int gsb_plan_level_tables(int nz, int nr, const double *r_row, double dr, double dz, int min_grid,
+                          int level, double *r_out, double *a_e_out, double *a_w_out,
+                          double *scalars_out /* dr,dz,a_ns,a_c */);
+
+/* Context: one grid geometry + workspace for up to batch_cap equilibria on one
+ * device.  r_row: HOST array of nr R-coordinates (an interior row of the
+ * reference's r_grid); dr,dz: the spacings exactly as the calling entry point
+ * computes them (SURVEY.md App.A item 1).  z_axis may be NULL when only the
+ * multigrid entry points are used. */
+int gsb_create(gsb_ctx **out, int nz, int nr, const double *r_row, const double *z_axis, double dr,
+               double dz, int batch_cap, int device);
+void gsb_destroy(gsb_ctx *ctx);
+
+/* --- multigrid operators (multigrid_solve.py) ---------------------------- */
+
+/* a1/a2: n_sweeps in-place red-black SOR sweeps (mg_smooth, multigrid_solve.py:148-208).
+ * clip!=0 adds the +-1e250 clamp of _sor_step (fusion_kernel_iterative_solver.py:158). */
+int gsb_smooth(gsb_ctx *ctx, double *psi_dev, const double *src_dev, int batch, double omega,
+               int n_sweeps, int clip, void *stream);
+/* a3: out-of-place toroidal Jacobi step with sanitise+clip (_jacobi_step, :54-95). */
+int gsb_jacobi(gsb_ctx *ctx, const double *psi_dev, const double *src_dev, double *out_dev,
+               int batch, void *stream);
+/* a4: r = L*psi - src on the interior, 0 on the wall (mg_residual, :211-249). */
+int gsb_residual(gsb_ctx *ctx, const double *psi_dev, const double *src_dev, double *res_dev,
+                 int batch, void *stream);
+/* a4: L*v (apply_gs_operator, fusion_kernel_solver_runtime.py:54-68). */
+int gsb_apply_operator(gsb_ctx *ctx, const double *v_dev, double *out_dev, int batch, void *stream);
+/* a5: per-equilibrium interior max|r| and RMS (residual_linf :338; compute_gs_residual_rms). */
+int gsb_residual_norms(gsb_ctx *ctx, const double *psi_dev, const double *src_dev,
+                       double *linf_dev, double *rms_dev, int batch, void *stream);
+/* a6/a7: geometry-free transfer operators on arbitrary shapes. */
+int gsb_restrict_full_weight(const double *fine_dev, double *coarse_dev, int nz_f, int nr_f,
+                             int batch, void *stream);
+int gsb_prolong_bilinear(const double *coarse_dev, double *fine_dev, int nz_c, int nr_c, int nz_f,
+                         int nr_f, int batch, void *stream);
+/* a8: one V-cycle, psi updated in place (multigrid_vcycle, :252-335; wall not re-applied). */
+int gsb_vcycle(gsb_ctx *ctx, double *psi_dev, const double *src_dev, int batch, double omega,
+               int pre, int post, int min_grid, void *stream);
+/* a9: V-cycles until interior Linf residual < tol (multigrid_solve, :352-463).
+ * psi_dev holds psi_bc on entry and the solution on exit; per-equilibrium outputs
+ * (device): residual, n_cycles, converged. */
+int gsb_mg_solve(gsb_ctx *ctx, const double *src_dev, double *psi_dev, int batch, double tol,
+                 int max_cycles, double omega, int pre, int post, int min_grid, double *res_dev,
+                 int *cycles_dev, int *converged_dev, void *stream);
+
+/* --- Picard pieces (fusion_kernel.py) ------------------------------------- */
+
+/* a10+a11: O-point (first global max, |psi|<1e-6 -> 1e-6) and X-point (first min of
+ * hypot(grad psi) over rows with Z < 0.5*z_min, optional 16-candidate saddle filter).
+ * out_dev: [batch][8] doubles = iz_ax, ir_ax, psi_ax, iz_x, ir_x, psi_x, found_x, min(psi).
+ * found_x==0: no row below 0.5*z_min -> the reference's ((0,0), min psi) fallback. */
+int gsb_topology(gsb_ctx *ctx, const double *psi_dev, int batch, double z_min, int saddle,
+                 double *out_dev, void *stream);
+
+typedef struct gsb_profile {
+  int hmode;         /* 0 = L-mode (1-psi_N), 1 = H-mode mtanh (fusion_kernel.py:359-390) */
+  double ped_p[4];   /* ped_top, ped_width, ped_height, core_alpha for p'  */
+  double ped_ff[4];  /* same for FF' */
+} gsb_profile;
+
+/* a12: J_phi(psi) renormalised to Ip (update_plasma_source_nonlinear, fusion_kernel.py:394-444).
+ * axis_bnd_dev: [batch][2] (psi_axis, psi_boundary); ip_dev: [batch];
+ * prof_dev: NULL (use `prof` for all) or [batch][8] per-equilibrium pedestal params. */
+int gsb_plasma_source(gsb_ctx *ctx, const double *psi_dev, const double *axis_bnd_dev,
+                      const double *ip_dev, double mu0, const gsb_profile *prof,
+                      const double *prof_dev, double *jphi_dev, int batch, void *stream);
+
+typedef struct gsb_picard_params {
+  int max_iterations;          /* solver.max_iterations */
+  double tol;                  /* solver.convergence_threshold */
+  double alpha;                /* solver.relaxation_factor (default 0.1) */
+  double omega;                /* solver.sor_omega (default 1.6) */
+  int method;                  /* 0 multigrid (default), 1 sor, 2 jacobi */
+  int require_gs_residual;     /* solver.require_gs_residual */
+  double gs_tol;               /* solver.gs_residual_threshold */
+  int saddle;                  /* solver.xpoint_use_saddle_detection */
+  double mu0;                  /* physics.vacuum_permeability */
+  double z_min, r_min, r_max;  /* dimensions.* (X-point mask, seed centre) */
+  int seed;                    /* 1: Gaussian seed + 50 Jacobi (_seed_plasma) */
+  int check_every;             /* host polls the active count every this many iterations */
+  gsb_profile prof;
+} gsb_picard_params;
+
+/* a13+a14: batched Picard solve (solve_equilibrium, fusion_kernel_newton_solver.py:390-615).
+ * psi_dev   [batch][nz][nr] in: initial flux (vacuum field or warm start), out: solution
+ * bc_dev    [batch][nz][nr] boundary map (only its wall ring is read)
+ * ip_dev    [batch]         plasma current targets
+ * prof_dev  NULL or [batch][8] per-equilibrium pedestal parameters
+ * jphi_dev  [batch][nz][nr] out: final J_phi
+ * summary_dev [batch][16] out: iterations, converged, residual(best diff), gs_residual,
+ *            gs_residual_best, status(0 run,1 conv,2 maxiter,3 diverged), psi_axis, psi_bnd,
+ *            iz_ax, ir_ax, iz_x, ir_x, diff_last, found_x, Ip/I scale, 0
+ * hist_dev / gs_hist_dev  NULL or [batch][max_iterations] histories */
+int gsb_picard_solve(gsb_ctx *ctx, const gsb_picard_params *p, double *psi_dev, const double *bc_dev,
+                     const double *ip_dev, const double *prof_dev, double *jphi_dev,
+                     double *summary_dev, double *hist_dev, double *gs_hist_dev, int batch,
+                     void *stream);
+/* Picard iterations launched by the last gsb_picard_solve on this ctx (host count). */
+int gsb_picard_last_launched_iterations(gsb_ctx *ctx);
+
+/* compute_b_field (fusion_kernel.py:450-456): np.gradient + 1/max(R,1e-6). */
+int gsb_b_field(gsb_ctx *ctx, const double *psi_dev, double *br_dev, double *bz_dev, int batch,
+                void *stream);
+
+/* --- Green's functions ---------------------------------------------------- */
+
+/* a15/a16: per-coil unit-current flux tables G[c][nz][nr] on the ctx grid.
+ * si==0: calculate_vacuum_field form (fusion_kernel.py:236-249, k2 clip, no self mask), two
+ *        planes per coil (see gsb_coil_flux), g_dev [n_coils][2][nz][nr];
+ * si==1: _green_function_vectorised (fusion_kernel_free_boundary.py:58-80) incl. mu0_SI and the
+ *        self-point mask, g_dev [n_coils][nz][nr].
+ * coil_rz: HOST [n_coils][2]. */
+int gsb_green_table(gsb_ctx *ctx, const double *coil_rz, int n_coils, int si, double *g_dev,
+                    void *stream);
+/* psi[b] = sum_c w[b][c] * G[c], accumulated in coil order from 0.0 (w_dev: [batch][n_coils]).
+ * si==0: g_dev is [c][2][nz][nr] = (sqrt(R Rc), ((2-k2)K-2E)/k), w = (mu0*I)/(2 pi), each term
+ *        evaluated as (w*sqrt)*term exactly like fusion_kernel.py:245-249;
+ * si==1: g_dev is [c][nz][nr], w = I*turns (fusion_kernel_free_boundary.py:88-92). */
+int gsb_coil_flux(gsb_ctx *ctx, const double *g_dev, const double *w_dev, int n_coils, int si,
+                  double *psi_dev, int batch, void *stream);
+/* a16: M[coil][point] = turns*G_SI (build_mutual_inductance_matrix, :137-153). HOST inputs. */
+int gsb_mutual_matrix(const double *coil_rz, const int *turns, int n_coils, const double *obs_rz,
+                      int n_pts, double *m_dev, void *stream);
+/* a18: lane-C von Hagenow response matrix M[N_wall][N_int] (build_response_matrix,
+ * jax_free_boundary_predictive.py:183-211; greens_psi_si, jax_free_boundary_gs.py:70-86). */
+int gsb_wall_matrix(gsb_ctx *ctx, double mu0, double *m_dev, void *stream);
+/* a18: wall[b][N_wall] = M @ (J[b][interior]*dA) (:498) as one FP64 tensor-core GEMM over the
+ * batch.  jphi_dev is the full (nz,nr) field; interior gather is fused. */
+int gsb_wall_flux(gsb_ctx *ctx, const double *m_dev, const double *jphi_dev, double dA,
+                  double *wall_dev, int batch, void *stream);
+/* Scatter wall[b][N_wall] (+ optional coil wall flux) onto the ring of bc_dev. */
+int gsb_wall_scatter(gsb_ctx *ctx, const double *wall_dev, double *bc_dev, int accumulate, int batch,
+                     void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSB200_H */

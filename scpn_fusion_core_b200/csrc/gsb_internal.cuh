@@ -1,0 +1,303 @@
+// gsb_internal.cuh - shared internals of libgsb200 (not part of the ABI).
+//
+// Conventions
+//   * fields are float64, C-order [b][iz][ir]; `n` = nz*nr is the per-equilibrium stride
+//   * element-wise arithmetic follows the reference's NumPy operand order and is kept
+//     free of FMA contraction (dmul/dadd/dsub wrappers) so that results are bit-identical
+//     to NumPy wherever NumPy's own result is defined by IEEE +,-,*,/ alone
+//   * divisions by per-level / per-column constants use the Markstein sequence
+//     q = a*y; r = fma(-b,q,a); q' = fma(r,y,q) with y = RN(1/b): correctly rounded (equals
+//     IEEE a/b; validated on 2e8 random operands) at 3 FP64 issue slots instead of ~25
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/gsb200.h"
+
+namespace gsb {
+
+// ---------------------------------------------------------------- errors / launch count
+void set_error(const std::string &msg);
+extern std::atomic<long long> g_launches;
+
+#define GSB_CUDA(call)                                                                      \
+  do {                                                                                      \
+    cudaError_t _e = (call);                                                                \
+    if (_e != cudaSuccess) {                                                                \
+      gsb::set_error(std::string(#call) + ": " + cudaGetErrorString(_e));                   \
+      return GSB_ECUDA;                                                                     \
+    }                                                                                       \
+  } while (0)
+
+#define GSB_LAUNCH_CHECK()                                                                  \
+  do {                                                                                      \
+    gsb::g_launches.fetch_add(1, std::memory_order_relaxed);                                \
+    cudaError_t _e = cudaGetLastError();                                                    \
+    if (_e != cudaSuccess) {                                                                \
+      gsb::set_error(std::string("kernel launch: ") + cudaGetErrorString(_e));              \
+      return GSB_ECUDA;                                                                     \
+    }                                                                                       \
+  } while (0)
+
+#define GSB_REQUIRE(cond, msg)                                                              \
+  do {                                                                                      \
+    if (!(cond)) {                                                                          \
+      gsb::set_error(msg);                                                                  \
+      return GSB_EINVAL;                                                                    \
+    }                                                                                       \
+  } while (0)
+
+// ---------------------------------------------------------------- exact FP64 helpers
+__device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
+// a / b with y = RN(1/b) precomputed; equals IEEE division for finite normal operands.
+__device__ __forceinline__ double ddiv_y(double a, double b, double y) {
+  double q = __dmul_rn(a, y);
+  double r = __fma_rn(-b, q, a);
+  double q2 = __fma_rn(r, y, q);
+  // non-finite a (inf/nan) or overflowed q: fall back to the plain quotient semantics
+  return (fabs(q) < 1.0e300 && fabs(a) < 1.0e300) ? q2 : __ddiv_rn(a, b);
+}
+
+constexpr double kCap = 1.0e250;  // fusion_kernel_numerics.py:16
+__device__ __forceinline__ double sanitize(double v) {
+  if (isnan(v)) return 0.0;
+  if (isinf(v)) return v > 0 ? kCap : -kCap;
+  return fmin(fmax(v, -kCap), kCap);
+}
+__device__ __forceinline__ double clip_cap(double v) {
+  // np.clip propagates NaN
+  if (isnan(v)) return v;
+  return fmin(fmax(v, -kCap), kCap);
+}
+
+// ---------------------------------------------------------------- level geometry
+// One multigrid level, passed by value to kernels.  Column tables live in device memory.
+struct LevelGeom {
+  int nz, nr;
+  double dr, dz;
+  double dr2, dz2, two_dr;              // residual denominators (multigrid_solve.py:243-245)
+  double inv_dr2, inv_dz2, inv_two_dr;  // their correctly rounded reciprocals
+  double a_ns, a_c, inv_a_c;            // multigrid_solve.py:188-189
+  const double *a_e;                    // [nr] 1/dr2 - 1/(2 R dr)   (interior columns)
+  const double *a_w;                    // [nr] 1/dr2 + 1/(2 R dr)
+  const double *r_safe;                 // [nr] max(R, 1e-10)
+  const double *inv_r_safe;             // [nr]
+};
+
+struct HostLevel {
+  int nz = 0, nr = 0;
+  double dr = 0, dz = 0;
+  std::vector<double> r_row, a_e, a_w, r_safe, inv_r_safe;
+  double a_ns = 0, a_c = 0;
+};
+
+// multigrid_solve.py:289-312 level recursion; r_row per level by the reference's
+// full-weighting of r_grid (interior rows).
+std::vector<HostLevel> plan_levels(int nz, int nr, const double *r_row, double dr, double dz,
+                                   int min_grid);
+
+// ---------------------------------------------------------------- stencil point functions
+// RB-SOR / Gauss-Seidel update, NumPy operand order (multigrid_solve.py:196-205)
+__device__ __forceinline__ double sor_point(const LevelGeom &g, double ae, double aw, double E,
+                                            double W, double S, double N, double src, double old,
+                                            double omega, double omw) {
+  double acc = dadd(dmul(ae, E), dmul(aw, W));
+  acc = dadd(acc, dmul(g.a_ns, S));
+  acc = dadd(acc, dmul(g.a_ns, N));
+  acc = dsub(acc, src);
+  const double gs = ddiv_y(acc, g.a_c, g.inv_a_c);
+  return dadd(dmul(omw, old), dmul(omega, gs));
+}
+
+// L psi = (E - 2C + W)/dr2 - ((E - W)/(2dr))/R + (N - 2C + S)/dz2   (multigrid_solve.py:243-247)
+__device__ __forceinline__ double gs_apply(const LevelGeom &g, int ir, double C, double E, double W,
+                                           double S, double N) {
+  const double twoC = dmul(2.0, C);
+  const double d2r = ddiv_y(dadd(dsub(E, twoC), W), g.dr2, g.inv_dr2);
+  const double d1r = ddiv_y(dsub(E, W), g.two_dr, g.inv_two_dr);
+  const double d2z = ddiv_y(dadd(dsub(N, twoC), S), g.dz2, g.inv_dz2);
+  return dadd(dsub(d2r, ddiv_y(d1r, g.r_safe[ir], g.inv_r_safe[ir])), d2z);
+}
+
+// ---------------------------------------------------------------- block reductions
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// Deterministic block-wide sum (fixed tree); result valid in thread 0.  `sh` >= 32 doubles.
+__device__ __forceinline__ double block_sum(double v, double *sh) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    v = lane < nw ? sh[lane] : 0.0;
+    v = warp_sum(v);
+  }
+  return v;
+}
+__device__ __forceinline__ double block_max(double v, double *sh) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int nw = (blockDim.x + 31) >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    v = lane < nw ? sh[lane] : -INFINITY;
+    v = warp_max(v);
+  }
+  return v;
+}
+// (value, index) extremum with first-occurrence tie-break (np.argmax / np.argmin order).
+struct ValIdx {
+  double v;
+  int i;
+};
+template <bool MAX>
+__device__ __forceinline__ ValIdx better(ValIdx a, ValIdx b) {
+  if (b.i < 0) return a;
+  if (a.i < 0) return b;
+  bool take_b = MAX ? (b.v > a.v) : (b.v < a.v);
+  if (b.v == a.v) take_b = b.i < a.i;
+  return take_b ? b : a;
+}
+template <bool MAX>
+__device__ __forceinline__ ValIdx warp_arg(ValIdx x) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ValIdx y;
+    y.v = __shfl_xor_sync(0xffffffffu, x.v, o);
+    y.i = __shfl_xor_sync(0xffffffffu, x.i, o);
+    x = better<MAX>(x, y);
+  }
+  return x;
+}
+template <bool MAX>
+__device__ __forceinline__ ValIdx block_arg(ValIdx x, double *shv, int *shi) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int nw = (blockDim.x + 31) >> 5;
+  x = warp_arg<MAX>(x);
+  __syncthreads();
+  if (lane == 0) {
+    shv[w] = x.v;
+    shi[w] = x.i;
+  }
+  __syncthreads();
+  if (w == 0) {
+    if (lane < nw) {
+      x.v = shv[lane];
+      x.i = shi[lane];
+    } else {
+      x.v = 0.0;
+      x.i = -1;
+    }
+    x = warp_arg<MAX>(x);
+  }
+  return x;
+}
+
+// glibc 2.39 hypot (sysdeps/ieee754/dbl-64/e_hypot.c, non-FMA kernel) restated with
+// IEEE +,-,*,/,sqrt only, so np.hypot is reproduced bit-for-bit (checked on 2e6 pairs).
+__device__ __forceinline__ double hypot_kernel(double ax, double ay) {
+  double h = __dsqrt_rn(dadd(dmul(ax, ax), dmul(ay, ay)));
+  double t1, t2;
+  if (h <= dmul(2.0, ay)) {
+    double delta = dsub(h, ay);
+    t1 = dmul(ax, dsub(dmul(2.0, delta), ax));
+    t2 = dmul(dsub(delta, dmul(2.0, dsub(ax, ay))), delta);
+  } else {
+    double delta = dsub(h, ax);
+    t1 = dmul(dmul(2.0, delta), dsub(ax, dmul(2.0, ay)));
+    t2 = dadd(dmul(dsub(dmul(4.0, delta), ay), ay), dmul(delta, delta));
+  }
+  return dsub(h, __ddiv_rn(dadd(t1, t2), dmul(2.0, h)));
+}
+__device__ __forceinline__ double hypot_glibc(double x, double y) {
+  if (isinf(x) || isinf(y)) return INFINITY;
+  if (isnan(x) || isnan(y)) return dadd(x, y);
+  x = fabs(x);
+  y = fabs(y);
+  double ax = x < y ? y : x;
+  double ay = x < y ? x : y;
+  if (ax > 0x1p+511) {  // LARGE_VAL: scale both inputs down
+    if (ay <= dmul(ax, 0x1p-54)) return dadd(ax, ay);
+    return dmul(hypot_kernel(dmul(ax, 0x1p-600), dmul(ay, 0x1p-600)), 0x1p+600);
+  }
+  if (ay < 0x1p-459) {  // TINY_VAL: scale both inputs up
+    if (ax >= dmul(ay, 0x1p+54)) return dadd(ax, ay);
+    return dmul(hypot_kernel(dmul(ax, 0x1p+600), dmul(ay, 0x1p+600)), 0x1p-600);
+  }
+  if (ax >= dmul(ay, 0x1p+54)) return dadd(ax, ay);
+  return hypot_kernel(ax, ay);
+}
+
+}  // namespace gsb
+
+// ---------------------------------------------------------------- context
+struct gsb_level_dev {
+  gsb::LevelGeom g;
+  double *tables = nullptr;  // one allocation: a_e | a_w | r_safe | inv_r_safe
+  double *d = nullptr;       // coarse right-hand side  [batch_cap][n]   (levels >= 1)
+  double *e = nullptr;       // coarse correction       [batch_cap][n]   (levels >= 1)
+};
+
+struct gsb_picard_ws;  // defined in gsb_picard.cu
+
+struct gsb_ctx {
+  int device = 0;
+  int nz = 0, nr = 0;
+  size_t n = 0;
+  int batch_cap = 0;
+  double dr = 0, dz = 0;
+  std::vector<double> r_row, z_axis;
+  int planned_min_grid = -1;
+  std::vector<gsb_level_dev> levels;
+  double *z_dev = nullptr;  // [nz]
+  double *r_dev = nullptr;  // [nr]
+  // scratch for reductions / mg_solve
+  double *red = nullptr;    // [batch_cap][kRedStride]
+  int *active = nullptr;    // [batch_cap]
+  int *counter = nullptr;   // device counter
+  int *h_counter = nullptr; // pinned host mirror
+  double *mg_bc = nullptr;  // wall ring copy for mg_solve [batch_cap][ring]
+  gsb_picard_ws *picard = nullptr;
+  int picard_last_iters = 0;
+  // lane-C wall indices
+  int n_wall = 0, n_int = 0;
+};
+
+namespace gsb {
+constexpr int kRedStride = 64;  // doubles of reduction scratch per equilibrium
+int ensure_plan(gsb_ctx *ctx, int min_grid);
+__host__ __device__ inline int ring_size(int nz, int nr) { return 2 * nr + 2 * nz; }
+// V-cycle on device (gsb_mg.cu); `active` may be NULL.
+int vcycle_launch(gsb_ctx *ctx, double *psi, size_t psi_stride, const double *src, int batch,
+                  double omega, int pre, int post, const int *active, cudaStream_t st);
+int smooth_launch(const LevelGeom &g, double *psi, size_t stride, const double *src, size_t sstride,
+                  int batch, double omega, int sweeps, int clip, const int *active, cudaStream_t st);
+int jacobi_launch(const LevelGeom &g, const double *psi, const double *src, double *out, int batch,
+                  const int *active, cudaStream_t st);
+int ring_save_launch(const double *f, size_t stride, double *ring, int nz, int nr, int batch,
+                     cudaStream_t st);
+int residual_norms_launch(gsb_ctx *ctx, const LevelGeom &g, const double *psi, size_t pstride,
+                          const double *src, size_t sstride, double *linf, double *rms, int batch,
+                          const int *active, cudaStream_t st);
+}  // namespace gsb

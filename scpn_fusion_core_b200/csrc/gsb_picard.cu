@@ -1,0 +1,879 @@
+// gsb_picard.cu - the batched Picard outer loop (a10-a14) on device.
+//
+// One launch sequence advances EVERY active equilibrium of the batch by one Picard iteration:
+//   T   k_topo          argmax psi, min psi, masked first-min of hypot(grad psi)   (a10, a11)
+//   TS  k_xpoint_saddle optional 16-candidate Hessian saddle filter               (a11)
+//   TF  k_topo_final    psi_axis / psi_boundary scalars (+ limiter fallback)       (:505)
+//   S1  k_source_raw    psi_N, profiles, J_raw, deterministic partial sums         (a12)
+//   S2  k_source_scale  J = J_raw*Ip/I ; Source = (-mu0*R)*J
+//   E   elliptic step   copy + V-cycle | SOR sweep | Jacobi                         (a8/a2/a3)
+//   R   k_relax         wall BC, NaN flag, mean|dpsi|, under-relaxation, GS residual (a13, a5)
+//   D   k_decide        history, best-state tracking, convergence, buffer rotation  (a13)
+// Per-equilibrium state lives in device arrays; the host only polls an active counter.
+#include "gsb_internal.cuh"
+
+constexpr int kPT = 8;   // max partial blocks per equilibrium
+constexpr int kTW = 8;   // doubles per topo partial
+constexpr int kRW = 4;   // doubles per relax partial
+
+struct PicardState {  // SoA, device pointers, [batch_cap] each
+  int *active, *status, *iter, *cur, *best, *nxt, *xsel, *seed_active;
+  double *diff_best, *gs_best, *gs_last, *diff_last, *scale;
+  double *axbnd;  // [b][2]
+  double *topo;   // [b][8]: iz_ax, ir_ax, psi_ax, iz_x, ir_x, psi_x, found, psi_min
+};
+
+struct Bufs {
+  double *p[3];
+};
+
+struct gsb_picard_ws {
+  int cap = 0;
+  double *buf1 = nullptr, *buf2 = nullptr, *W = nullptr, *source = nullptr, *ring = nullptr;
+  double *tpart = nullptr, *spart = nullptr, *rpart = nullptr;
+  double *seedJ = nullptr, *cf = nullptr, *mr = nullptr;
+  int *rowmask = nullptr;
+  int *ints = nullptr;
+  double *dbls = nullptr;
+  PicardState s{};
+  // cached host-side parameters the device tables were built for
+  double mu0 = NAN, z_min = NAN, r_min = NAN, r_max = NAN;
+  double seed_sum = 0.0;
+};
+
+namespace gsb {
+
+struct GradGeom {
+  double dz, dr, two_dz, two_dr, inv_dz, inv_dr, inv_two_dz, inv_two_dr;
+};
+
+// np.gradient semantics (2nd-order centred interior, 1st-order one-sided edges), uniform spacing
+__device__ __forceinline__ void grad_point(const double *__restrict__ f, int nz, int nr, int iz,
+                                           int ir, const GradGeom &gg, double &gz, double &gr) {
+  const double *p = f + (size_t)iz * nr + ir;
+  if (iz == 0)
+    gz = ddiv_y(dsub(p[nr], p[0]), gg.dz, gg.inv_dz);
+  else if (iz == nz - 1)
+    gz = ddiv_y(dsub(p[0], p[-nr]), gg.dz, gg.inv_dz);
+  else
+    gz = ddiv_y(dsub(p[nr], p[-nr]), gg.two_dz, gg.inv_two_dz);
+  if (ir == 0)
+    gr = ddiv_y(dsub(p[1], p[0]), gg.dr, gg.inv_dr);
+  else if (ir == nr - 1)
+    gr = ddiv_y(dsub(p[0], p[-1]), gg.dr, gg.inv_dr);
+  else
+    gr = ddiv_y(dsub(p[1], p[-1]), gg.two_dr, gg.inv_two_dr);
+}
+
+static GradGeom make_grad_geom(double dz, double dr) {
+  GradGeom g;
+  volatile double tz = 2.0 * dz, tr = 2.0 * dr;
+  g.dz = dz;
+  g.dr = dr;
+  g.two_dz = tz;
+  g.two_dr = tr;
+  g.inv_dz = 1.0 / dz;
+  g.inv_dr = 1.0 / dr;
+  g.inv_two_dz = 1.0 / tz;
+  g.inv_two_dr = 1.0 / tr;
+  return g;
+}
+
+// ---------------------------------------------------------------------------- T
+__global__ void __launch_bounds__(256)
+k_topo(Bufs bufs, const int *__restrict__ cur, size_t n, int nz, int nr, GradGeom gg,
+       const int *__restrict__ rowmask, double *__restrict__ tpart, const int *__restrict__ active) {
+  __shared__ double shv[32];
+  __shared__ int shi[32];
+  const int b = blockIdx.y, P = gridDim.x, p = blockIdx.x;
+  if (active && !active[b]) return;
+  const double *f = bufs.p[cur ? cur[b] : 0] + (size_t)b * n;
+  const int r0 = (int)((long long)nz * p / P), r1 = (int)((long long)nz * (p + 1) / P);
+  ValIdx mx{0.0, -1}, mb{0.0, -1};
+  double mn = INFINITY;
+  for (int idx = threadIdx.x; idx < (r1 - r0) * nr; idx += blockDim.x) {
+    const int iz = r0 + idx / nr, ir = idx % nr;
+    const int flat = iz * nr + ir;
+    const double v = f[flat];
+    mx = better<true>(mx, ValIdx{v, flat});
+    mn = fmin(mn, v);
+    if (rowmask[iz]) {
+      double gz, gr;
+      grad_point(f, nz, nr, iz, ir, gg, gz, gr);
+      const double bm = hypot_glibc(gr, gz);
+      if (isfinite(bm)) mb = better<false>(mb, ValIdx{bm, flat});
+    }
+  }
+  mx = block_arg<true>(mx, shv, shi);
+  __syncthreads();
+  mb = block_arg<false>(mb, shv, shi);
+  __syncthreads();
+  const double mnb = -block_max(-mn, shv);
+  if (threadIdx.x == 0) {
+    double *o = tpart + ((size_t)b * kPT + p) * kTW;
+    o[0] = mx.v;
+    o[1] = (double)mx.i;
+    o[2] = mb.v;
+    o[3] = (double)mb.i;
+    o[4] = mnb;
+  }
+}
+
+// ---------------------------------------------------------------------------- TS
+// fusion_kernel.py:295-337: among the (up to) 16 smallest masked |grad psi| keep true saddles
+// (Hessian determinant < 0, interior only) and take the one with the smallest |grad psi|.
+__global__ void __launch_bounds__(256)
+k_xpoint_saddle(Bufs bufs, const int *__restrict__ cur, size_t n, int nz, int nr, GradGeom gg,
+                double dr2, double dz2, double four_drdz, const int *__restrict__ rowmask,
+                int *__restrict__ xsel, const int *__restrict__ active) {
+  __shared__ double shv[32];
+  __shared__ int shi[32];
+  __shared__ double prev_v;
+  __shared__ int prev_i, best_i;
+  __shared__ double best_v;
+  const int b = blockIdx.x;
+  if (active && !active[b]) return;
+  const double *f = bufs.p[cur ? cur[b] : 0] + (size_t)b * n;
+  if (threadIdx.x == 0) {
+    prev_v = -1.0;
+    prev_i = -1;
+    best_i = -1;
+    best_v = INFINITY;
+  }
+  __syncthreads();
+  for (int round = 0; round < 16; ++round) {
+    const double pv = prev_v;
+    const int pi = prev_i;
+    ValIdx mb{0.0, -1};
+    for (int flat = threadIdx.x; flat < nz * nr; flat += blockDim.x) {
+      const int iz = flat / nr, ir = flat - iz * nr;
+      if (!rowmask[iz]) continue;
+      double gz, gr;
+      grad_point(f, nz, nr, iz, ir, gg, gz, gr);
+      const double bm = hypot_glibc(gr, gz);
+      if (!isfinite(bm)) continue;
+      // strictly after (pv, pi) in (value, index) lexicographic order
+      if (bm < pv || (bm == pv && flat <= pi)) continue;
+      mb = better<false>(mb, ValIdx{bm, flat});
+    }
+    mb = block_arg<false>(mb, shv, shi);
+    if (threadIdx.x == 0) {
+      prev_v = mb.v;
+      prev_i = mb.i;
+      if (mb.i >= 0) {
+        const int iz = mb.i / nr, ir = mb.i - iz * nr;
+        if (iz > 0 && iz < nz - 1 && ir > 0 && ir < nr - 1) {
+          const double *q = f + mb.i;
+          const double c2 = dmul(2.0, q[0]);
+          const double d2r = __ddiv_rn(dadd(dsub(q[1], c2), q[-1]), dr2);
+          const double d2z = __ddiv_rn(dadd(dsub(q[nr], c2), q[-nr]), dz2);
+          const double drz = __ddiv_rn(
+              dadd(dsub(dsub(q[nr + 1], q[nr - 1]), q[-nr + 1]), q[-nr - 1]), four_drdz);
+          const double det = dsub(dmul(d2r, d2z), dmul(drz, drz));
+          if (isfinite(det) && det < 0.0 && mb.v < best_v) {
+            best_v = mb.v;
+            best_i = mb.i;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    if (prev_i < 0) break;
+  }
+  if (threadIdx.x == 0) xsel[b] = best_i;
+}
+
+// ---------------------------------------------------------------------------- TF
+__global__ void k_topo_final(Bufs bufs, const int *__restrict__ cur, size_t n, int nr, int P,
+                             const double *__restrict__ tpart, const int *__restrict__ xsel,
+                             double *__restrict__ topo, double *__restrict__ axbnd, int limiter,
+                             int batch, const int *__restrict__ active) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  if (active && !active[b]) return;
+  const double *f = bufs.p[cur ? cur[b] : 0] + (size_t)b * n;
+  ValIdx mx{0.0, -1}, mb{0.0, -1};
+  double mn = INFINITY;
+  for (int p = 0; p < P; ++p) {
+    const double *o = tpart + ((size_t)b * kPT + p) * kTW;
+    mx = better<true>(mx, ValIdx{o[0], (int)o[1]});
+    mb = better<false>(mb, ValIdx{o[2], (int)o[3]});
+    mn = fmin(mn, o[4]);
+  }
+  double psi_ax = mx.v;
+  if (fabs(psi_ax) < 1e-6) psi_ax = 1e-6;  // fusion_kernel.py:353
+  int xi = mb.i;
+  if (xsel && xsel[b] >= 0) xi = xsel[b];
+  double psi_x, found;
+  int izx = 0, irx = 0;
+  if (xi >= 0) {
+    psi_x = f[xi];
+    izx = xi / nr;
+    irx = xi - izx * nr;
+    found = 1.0;
+  } else {  // no divertor rows / nothing finite: ((0,0), min psi)  (fusion_kernel.py:339-340)
+    psi_x = mn;
+    found = 0.0;
+  }
+  double *t = topo + (size_t)b * 8;
+  t[0] = (double)(mx.i / nr);
+  t[1] = (double)(mx.i % nr);
+  t[2] = psi_ax;
+  t[3] = (double)izx;
+  t[4] = (double)irx;
+  t[5] = psi_x;
+  t[6] = found;
+  t[7] = mn;
+  if (axbnd) {
+    double pb = psi_x;
+    if (limiter && fabs(dsub(psi_ax, pb)) < 0.1) pb = dmul(psi_ax, 0.1);  // newton_solver.py:505
+    axbnd[2 * b] = psi_ax;
+    axbnd[2 * b + 1] = pb;
+  }
+}
+
+// ---------------------------------------------------------------------------- S1 / S2
+struct ProfileDev {
+  int hmode;
+  double p[4], f[4];
+};
+
+__device__ __forceinline__ double mtanh_dev(double x, const double *q) {
+  // fusion_kernel.py:380-389 (caller guarantees 0 <= x < 1)
+  double y = __ddiv_rn(dsub(q[0], x), q[1]);
+  y = fmin(fmax(y, -20.0), 20.0);
+  const double ped = dmul(dmul(0.5, q[2]), dadd(1.0, tanh(y)));
+  double core = 0.0;
+  if (x < q[0]) {
+    const double t = __ddiv_rn(x, q[0]);
+    core = fmax(0.0, dsub(1.0, dmul(t, t)));
+  }
+  return dadd(ped, dmul(q[3], core));
+}
+
+__global__ void __launch_bounds__(256)
+k_source_raw(Bufs bufs, const int *__restrict__ cur, size_t n, int nz, int nr,
+             const double *__restrict__ axbnd, ProfileDev prof, const double *__restrict__ prof_dev,
+             const double *__restrict__ rrow, const double *__restrict__ cf,
+             double *__restrict__ jraw, double *__restrict__ spart, const int *__restrict__ active) {
+  __shared__ double sh[32];
+  const int b = blockIdx.y, P = gridDim.x, p = blockIdx.x;
+  if (active && !active[b]) return;
+  const double *f = bufs.p[cur ? cur[b] : 0] + (size_t)b * n;
+  const double psi_ax = axbnd[2 * b];
+  double denom = dsub(axbnd[2 * b + 1], psi_ax);
+  if (fabs(denom) < 1e-9) denom = 1e-9;
+  const double inv_denom = __ddiv_rn(1.0, denom);
+  double pp[4], pf[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    pp[i] = prof_dev ? prof_dev[(size_t)b * 8 + i] : prof.p[i];
+    pf[i] = prof_dev ? prof_dev[(size_t)b * 8 + 4 + i] : prof.f[i];
+  }
+  const int r0 = (int)((long long)nz * p / P), r1 = (int)((long long)nz * (p + 1) / P);
+  double acc = 0.0;
+  for (int idx = threadIdx.x; idx < (r1 - r0) * nr; idx += blockDim.x) {
+    const int iz = r0 + idx / nr, ir = idx % nr;
+    const size_t o = (size_t)iz * nr + ir;
+    const double pn = ddiv_y(dsub(f[o], psi_ax), denom, inv_denom);
+    const bool in = (pn >= 0.0) && (pn < 1.0);
+    double pr = 0.0, ff = 0.0;
+    if (in) {
+      if (prof.hmode) {
+        pr = mtanh_dev(pn, pp);
+        ff = mtanh_dev(pn, pf);
+      } else {
+        pr = dsub(1.0, pn);
+        ff = pr;
+      }
+    }
+    // J_raw = 0.5*(R*p) + 0.5*((1/(mu0 R))*ff)      (fusion_kernel.py:430-434)
+    const double j = dadd(dmul(0.5, dmul(rrow[ir], pr)), dmul(0.5, dmul(cf[ir], ff)));
+    jraw[(size_t)b * n + o] = j;
+    acc += j;
+  }
+  acc = block_sum(acc, sh);
+  if (threadIdx.x == 0) spart[(size_t)b * kPT + p] = acc;
+}
+
+__global__ void __launch_bounds__(256)
+k_source_scale(size_t n, int nz, int nr, double dr, double dz, const double *__restrict__ ip,
+               const double *__restrict__ spart, int P, const double *__restrict__ mr,
+               double *__restrict__ jphi, double *__restrict__ source, double *__restrict__ scale_out,
+               const int *__restrict__ active) {
+  const int b = blockIdx.y, p = blockIdx.x;
+  if (active && !active[b]) return;
+  double s = 0.0;
+  for (int q = 0; q < P; ++q) s += spart[(size_t)b * kPT + q];
+  const double icur = dmul(dmul(s, dr), dz);  // float(np.sum(J_raw)) * dR * dZ
+  const bool ok = fabs(icur) > 1e-9;
+  const double sc = ok ? __ddiv_rn(ip[b], icur) : 0.0;
+  if (scale_out && p == 0 && threadIdx.x == 0) scale_out[b] = sc;
+  const int r0 = (int)((long long)nz * p / gridDim.x), r1 = (int)((long long)nz * (p + 1) / gridDim.x);
+  for (int idx = threadIdx.x; idx < (r1 - r0) * nr; idx += blockDim.x) {
+    const int iz = r0 + idx / nr, ir = idx % nr;
+    const size_t o = (size_t)b * n + (size_t)iz * nr + ir;
+    const double j = ok ? dmul(jphi[o], sc) : 0.0;
+    jphi[o] = j;
+    if (source) source[o] = dmul(mr[ir], j);  // (-mu0*R)*J
+  }
+}
+
+// ---------------------------------------------------------------------------- E helpers
+__global__ void __launch_bounds__(256)
+k_copy_from_cur(Bufs bufs, const int *__restrict__ cur, size_t n, double *__restrict__ dst,
+                int do_sanitize, const int *__restrict__ active) {
+  const int b = blockIdx.y;
+  if (active && !active[b]) return;
+  const double *f = bufs.p[cur ? cur[b] : 0] + (size_t)b * n;
+  double *d = dst + (size_t)b * n;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    d[i] = do_sanitize ? sanitize(f[i]) : f[i];
+}
+
+__global__ void __launch_bounds__(256)
+k_jacobi_from_cur(LevelGeom g, Bufs bufs, const int *__restrict__ cur, const double *__restrict__ src,
+                  double *__restrict__ out, const int *__restrict__ active) {
+  const int b = blockIdx.z;
+  if (active && !active[b]) return;
+  const int ir = blockIdx.x * blockDim.x + threadIdx.x;
+  const int iz = blockIdx.y * blockDim.y + threadIdx.y;
+  if (ir >= g.nr || iz >= g.nz) return;
+  const size_t n = (size_t)g.nz * g.nr;
+  const double *p = bufs.p[cur[b]] + b * n + (size_t)iz * g.nr + ir;
+  double v;
+  if (iz == 0 || ir == 0 || iz == g.nz - 1 || ir == g.nr - 1) {
+    v = sanitize(p[0]);
+  } else {
+    double acc = dadd(dmul(g.a_e[ir], sanitize(p[1])), dmul(g.a_w[ir], sanitize(p[-1])));
+    acc = dadd(acc, dmul(g.a_ns, sanitize(p[-g.nr])));
+    acc = dadd(acc, dmul(g.a_ns, sanitize(p[g.nr])));
+    acc = dsub(acc, sanitize(src[b * n + (size_t)iz * g.nr + ir]));
+    v = clip_cap(ddiv_y(acc, g.a_c, g.inv_a_c));
+  }
+  out[b * n + (size_t)iz * g.nr + ir] = v;
+}
+
+// ---------------------------------------------------------------------------- R
+// ring layout as in gsb_mg.cu: [row0][row nz-1][col0][col nr-1]
+__device__ __forceinline__ double wall_or(const double *__restrict__ W, const double *__restrict__ ring,
+                                          int nz, int nr, int iz, int ir) {
+  if (ir == 0) return ring[2 * nr + iz];
+  if (ir == nr - 1) return ring[2 * nr + nz + iz];
+  if (iz == 0) return ring[ir];
+  if (iz == nz - 1) return ring[nr + ir];
+  return W[(size_t)iz * nr + ir];
+}
+
+__global__ void __launch_bounds__(256)
+k_relax(LevelGeom g, Bufs bufs, const int *__restrict__ cur, const int *__restrict__ nxt,
+        const double *__restrict__ Wall, const double *__restrict__ ringall,
+        const double *__restrict__ srcall, double alpha, double oma, double *__restrict__ rpart,
+        const int *__restrict__ active) {
+  __shared__ double sh[32];
+  const int b = blockIdx.y, P = gridDim.x, p = blockIdx.x;
+  if (active && !active[b]) return;
+  const int nz = g.nz, nr = g.nr;
+  const size_t n = (size_t)nz * nr;
+  const double *f = bufs.p[cur[b]] + b * n;
+  double *out = bufs.p[nxt[b]] + b * n;
+  const double *W = Wall + b * n;
+  const double *ring = ringall + (size_t)b * ring_size(nz, nr);
+  const double *src = srcall + b * n;
+  const int r0 = (int)((long long)nz * p / P), r1 = (int)((long long)nz * (p + 1) / P);
+  double dsum = 0.0, rmax = 0.0, rsq = 0.0;
+  int bad = 0;
+  for (int idx = threadIdx.x; idx < (r1 - r0) * nr; idx += blockDim.x) {
+    const int iz = r0 + idx / nr, ir = idx % nr;
+    const size_t o = (size_t)iz * nr + ir;
+    const double wn = wall_or(W, ring, nz, nr, iz, ir);
+    const double old = f[o];
+    if (isnan(wn) || isinf(wn)) bad = 1;
+    dsum += fabs(dsub(wn, old));
+    const double c = dadd(dmul(oma, old), dmul(alpha, wn));  // (1-a)*Psi + a*Psi_new
+    out[o] = c;
+    if (iz > 0 && ir > 0 && iz < nz - 1 && ir < nr - 1) {
+      const double e = dadd(dmul(oma, f[o + 1]), dmul(alpha, wall_or(W, ring, nz, nr, iz, ir + 1)));
+      const double w = dadd(dmul(oma, f[o - 1]), dmul(alpha, wall_or(W, ring, nz, nr, iz, ir - 1)));
+      const double s = dadd(dmul(oma, f[o - nr]), dmul(alpha, wall_or(W, ring, nz, nr, iz - 1, ir)));
+      const double nn = dadd(dmul(oma, f[o + nr]), dmul(alpha, wall_or(W, ring, nz, nr, iz + 1, ir)));
+      const double r = dsub(gs_apply(g, ir, c, e, w, s, nn), src[o]);
+      const double a = fabs(r);
+      if (a > rmax) rmax = a;
+      rsq += r * r;
+    }
+  }
+  const int anybad = __syncthreads_or(bad);
+  dsum = block_sum(dsum, sh);
+  __syncthreads();
+  rmax = block_max(rmax, sh);
+  __syncthreads();
+  rsq = block_sum(rsq, sh);
+  if (threadIdx.x == 0) {
+    double *o = rpart + ((size_t)b * kPT + p) * kRW;
+    o[0] = dsum;
+    o[1] = anybad ? 1.0 : 0.0;
+    o[2] = rmax;
+    o[3] = rsq;
+  }
+}
+
+// ---------------------------------------------------------------------------- D
+__global__ void k_decide(PicardState s, const double *__restrict__ rpart, int P, double n_all,
+                         double n_int, double tol, int need_gs, double gs_tol, int max_iter,
+                         double *__restrict__ hist, double *__restrict__ gs_hist,
+                         int *__restrict__ counter, int batch) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  if (!s.active[b]) return;
+  double dsum = 0.0, rmax = 0.0, rsq = 0.0;
+  bool bad = false;
+  for (int p = 0; p < P; ++p) {
+    const double *o = rpart + ((size_t)b * kPT + p) * kRW;
+    dsum += o[0];
+    bad = bad || (o[1] != 0.0);
+    rmax = fmax(rmax, o[2]);
+    rsq += o[3];
+  }
+  const int k = s.iter[b];
+  if (bad) {  // NaN/Inf in Psi_new: revert to the best state and stop (newton_solver.py:518-532)
+    s.status[b] = 3;
+    s.iter[b] = k + 1;
+    s.active[b] = 0;
+    s.cur[b] = s.best[b];
+    return;
+  }
+  const double diff = dsum / n_all;
+  const double gs = (rmax > 0.0 && n_int > 0.0) ? sqrt(rsq / n_int) : 0.0;
+  if (hist) hist[(size_t)b * max_iter + k] = diff;
+  if (gs_hist) gs_hist[(size_t)b * max_iter + k] = gs;
+  s.diff_last[b] = diff;
+  s.gs_last[b] = gs;
+  if (gs < s.gs_best[b]) s.gs_best[b] = gs;
+  const int newcur = s.nxt[b];
+  int best = s.best[b];
+  if (diff < s.diff_best[b]) {
+    s.diff_best[b] = diff;
+    best = newcur;
+  }
+  s.cur[b] = newcur;
+  s.best[b] = best;
+  s.nxt[b] = (newcur == best) ? (newcur + 1) % 3 : 3 - newcur - best;
+  s.iter[b] = k + 1;
+  const bool conv = (diff < tol) && (!need_gs || gs < gs_tol);
+  if (conv) {
+    s.status[b] = 1;
+    s.active[b] = 0;
+  } else if (k + 1 >= max_iter) {
+    s.status[b] = 2;
+    s.active[b] = 0;
+  } else {
+    atomicAdd(counter, 1);
+  }
+}
+
+__global__ void k_picard_init(PicardState s, int batch, int best0, const double *__restrict__ ip,
+                              int seed) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  s.active[b] = 1;
+  s.status[b] = 0;
+  s.iter[b] = 0;
+  s.cur[b] = 0;
+  s.best[b] = best0;
+  s.nxt[b] = 1;
+  s.xsel[b] = -1;
+  s.seed_active[b] = (seed && fabs(ip[b]) >= 1e-12) ? 1 : 0;
+  s.diff_best[b] = 1e9;
+  s.gs_best[b] = INFINITY;
+  s.gs_last[b] = INFINITY;
+  s.diff_last[b] = 0.0;
+  s.scale[b] = 0.0;
+}
+
+// seed source: Source0 = (-mu0 R) * (seedJ * Ip/I_seed)   (fusion_kernel_iterative_solver.py:400-408)
+__global__ void __launch_bounds__(256)
+k_seed_source(size_t n, int nr, const double *__restrict__ seedJ, double seed_sum_drdz,
+              const double *__restrict__ ip, const double *__restrict__ mr,
+              double *__restrict__ jphi, double *__restrict__ source,
+              const int *__restrict__ seed_active) {
+  const int b = blockIdx.y;
+  if (!seed_active[b]) return;
+  const double sc = seed_sum_drdz > 0.0 ? __ddiv_rn(ip[b], seed_sum_drdz) : 1.0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const double j = dmul(seedJ[i], sc);
+    jphi[(size_t)b * n + i] = j;
+    source[(size_t)b * n + i] = dmul(mr[i % nr], j);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_finalize(Bufs bufs, PicardState s, size_t n, double *__restrict__ summary, int batch) {
+  const int b = blockIdx.y;
+  const int c = s.cur[b];
+  if (c != 0) {
+    const double *f = bufs.p[c] + (size_t)b * n;
+    double *d = bufs.p[0] + (size_t)b * n;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+      d[i] = f[i];
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && summary) {
+    double *o = summary + (size_t)b * 16;
+    const double *t = s.topo + (size_t)b * 8;
+    o[0] = (double)s.iter[b];
+    o[1] = s.status[b] == 1 ? 1.0 : 0.0;
+    o[2] = s.diff_best[b];
+    o[3] = s.gs_last[b];
+    o[4] = s.gs_best[b];
+    o[5] = (double)s.status[b];
+    o[6] = s.axbnd[2 * b];
+    o[7] = s.axbnd[2 * b + 1];
+    o[8] = t[0];
+    o[9] = t[1];
+    o[10] = t[3];
+    o[11] = t[4];
+    o[12] = s.diff_last[b];
+    o[13] = t[6];
+    o[14] = s.scale[b];
+    o[15] = 0.0;
+  }
+}
+
+// compute_b_field (fusion_kernel.py:450-456)
+__global__ void __launch_bounds__(256)
+k_bfield(const double *__restrict__ psi, int nz, int nr, GradGeom gg, const double *__restrict__ rrow,
+         double *__restrict__ br, double *__restrict__ bz) {
+  const int b = blockIdx.z;
+  const int ir = blockIdx.x * blockDim.x + threadIdx.x;
+  const int iz = blockIdx.y * blockDim.y + threadIdx.y;
+  if (ir >= nr || iz >= nz) return;
+  const size_t n = (size_t)nz * nr;
+  double gz, gr;
+  grad_point(psi + b * n, nz, nr, iz, ir, gg, gz, gr);
+  const double rs = fmax(rrow[ir], 1e-6);
+  const double inv = __ddiv_rn(1.0, rs);
+  br[b * n + (size_t)iz * nr + ir] = dmul(-inv, gz);
+  bz[b * n + (size_t)iz * nr + ir] = dmul(inv, gr);
+}
+
+}  // namespace gsb
+
+using namespace gsb;
+
+// numpy's pairwise summation for a contiguous float64 buffer (used for the seed integral)
+static double np_pairwise_sum(const double *a, size_t n) {
+  if (n < 8) {
+    double r = 0.0;
+    for (size_t i = 0; i < n; ++i) r += a[i];
+    return r;
+  }
+  if (n <= 128) {
+    volatile double r[8];
+    for (int j = 0; j < 8; ++j) r[j] = a[j];
+    size_t i;
+    for (i = 8; i < n - (n % 8); i += 8)
+      for (int j = 0; j < 8; ++j) r[j] = r[j] + a[i + j];
+    volatile double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    for (; i < n; ++i) res = res + a[i];
+    return res;
+  }
+  size_t n2 = n / 2;
+  n2 -= n2 % 8;
+  volatile double s1 = np_pairwise_sum(a, n2);
+  volatile double s2 = np_pairwise_sum(a + n2, n - n2);
+  return s1 + s2;
+}
+
+static int picard_ws_ensure(gsb_ctx *ctx, const gsb_picard_params *p) {
+  if (!ctx->picard) {
+    auto *w = new gsb_picard_ws();
+    ctx->picard = w;
+    w->cap = ctx->batch_cap;
+    const size_t N = ctx->n * (size_t)w->cap * sizeof(double);
+    GSB_CUDA(cudaMalloc(&w->buf1, N));
+    GSB_CUDA(cudaMalloc(&w->buf2, N));
+    GSB_CUDA(cudaMalloc(&w->W, N));
+    GSB_CUDA(cudaMalloc(&w->source, N));
+    GSB_CUDA(cudaMalloc(&w->ring, (size_t)w->cap * ring_size(ctx->nz, ctx->nr) * sizeof(double)));
+    GSB_CUDA(cudaMalloc(&w->tpart, (size_t)w->cap * kPT * kTW * sizeof(double)));
+    GSB_CUDA(cudaMalloc(&w->spart, (size_t)w->cap * kPT * sizeof(double)));
+    GSB_CUDA(cudaMalloc(&w->rpart, (size_t)w->cap * kPT * kRW * sizeof(double)));
+    GSB_CUDA(cudaMalloc(&w->seedJ, ctx->n * sizeof(double)));
+    GSB_CUDA(cudaMalloc(&w->cf, ctx->nr * sizeof(double)));
+    GSB_CUDA(cudaMalloc(&w->mr, ctx->nr * sizeof(double)));
+    GSB_CUDA(cudaMalloc(&w->rowmask, ctx->nz * sizeof(int)));
+    GSB_CUDA(cudaMalloc(&w->ints, (size_t)w->cap * 8 * sizeof(int)));
+    GSB_CUDA(cudaMalloc(&w->dbls, (size_t)w->cap * (5 + 2 + 8) * sizeof(double)));
+    const size_t c = w->cap;
+    PicardState &s = w->s;
+    s.active = w->ints;
+    s.status = w->ints + c;
+    s.iter = w->ints + 2 * c;
+    s.cur = w->ints + 3 * c;
+    s.best = w->ints + 4 * c;
+    s.nxt = w->ints + 5 * c;
+    s.xsel = w->ints + 6 * c;
+    s.seed_active = w->ints + 7 * c;
+    s.diff_best = w->dbls;
+    s.gs_best = w->dbls + c;
+    s.gs_last = w->dbls + 2 * c;
+    s.diff_last = w->dbls + 3 * c;
+    s.scale = w->dbls + 4 * c;
+    s.axbnd = w->dbls + 5 * c;
+    s.topo = w->dbls + 7 * c;
+  }
+  gsb_picard_ws *w = ctx->picard;
+  const bool same = (w->mu0 == p->mu0) && (w->z_min == p->z_min) && (w->r_min == p->r_min) && (w->r_max == p->r_max);
+  if (!same) {
+    const int nz = ctx->nz, nr = ctx->nr;
+    GSB_REQUIRE((int)ctx->z_axis.size() == nz, "gsb_picard_solve: context was created without a z axis");
+    std::vector<double> cf(nr), mr(nr), seed(ctx->n);
+    std::vector<int> mask(nz);
+    for (int j = 0; j < nr; ++j) {
+      volatile double m = p->mu0 * ctx->r_row[j];
+      cf[j] = 1.0 / m;                    // 1.0 / (mu0 * RR)
+      volatile double nm = -p->mu0;
+      mr[j] = nm * ctx->r_row[j];         // (-mu0) * RR
+    }
+    volatile double half_zmin = p->z_min * 0.5;
+    for (int i = 0; i < nz; ++i) mask[i] = (half_zmin > ctx->z_axis[i]) ? 1 : 0;
+    volatile double rc = (p->r_min + p->r_max) / 2.0;
+    for (int i = 0; i < nz; ++i)
+      for (int j = 0; j < nr; ++j) {
+        volatile double a = ctx->r_row[j] - rc;
+        volatile double a2 = a * a;
+        volatile double z2 = ctx->z_axis[i] * ctx->z_axis[i];
+        volatile double d = a2 + z2;
+        volatile double arg = -d;
+        volatile double arg2 = arg / 2.0;
+        seed[(size_t)i * nr + j] = std::exp(arg2);
+      }
+    w->seed_sum = np_pairwise_sum(seed.data(), seed.size());
+    GSB_CUDA(cudaMemcpy(w->cf, cf.data(), nr * sizeof(double), cudaMemcpyHostToDevice));
+    GSB_CUDA(cudaMemcpy(w->mr, mr.data(), nr * sizeof(double), cudaMemcpyHostToDevice));
+    GSB_CUDA(cudaMemcpy(w->rowmask, mask.data(), nz * sizeof(int), cudaMemcpyHostToDevice));
+    GSB_CUDA(cudaMemcpy(w->seedJ, seed.data(), seed.size() * sizeof(double), cudaMemcpyHostToDevice));
+    w->mu0 = p->mu0;
+    w->z_min = p->z_min;
+    w->r_min = p->r_min;
+    w->r_max = p->r_max;
+  }
+  return GSB_OK;
+}
+
+static int partials_for(int nz, int nr) {
+  long long pts = (long long)nz * nr;
+  int P = (int)((pts + 4095) / 4096);
+  if (P < 1) P = 1;
+  if (P > kPT) P = kPT;
+  if (P > nz) P = nz;
+  return P;
+}
+
+static ProfileDev to_dev(const gsb_profile &q) {
+  ProfileDev d;
+  d.hmode = q.hmode;
+  for (int i = 0; i < 4; ++i) {
+    d.p[i] = q.ped_p[i];
+    d.f[i] = q.ped_ff[i];
+  }
+  return d;
+}
+
+extern "C" {
+
+void gsb_picard_ws_free(gsb_ctx *ctx) {
+  gsb_picard_ws *w = ctx->picard;
+  if (!w) return;
+  void *ptrs[] = {w->buf1, w->buf2, w->W, w->source, w->ring, w->tpart, w->spart, w->rpart,
+                  w->seedJ, w->cf, w->mr, w->rowmask, w->ints, w->dbls};
+  for (void *q : ptrs)
+    if (q) cudaFree(q);
+  delete w;
+  ctx->picard = nullptr;
+}
+
+int gsb_topology(gsb_ctx *ctx, const double *psi_dev, int batch, double z_min, int saddle,
+                 double *out_dev, void *stream) {
+  GSB_REQUIRE(ctx && psi_dev && out_dev, "gsb_topology: NULL argument");
+  GSB_REQUIRE(batch >= 1 && batch <= ctx->batch_cap, "gsb_topology: batch outside [1, batch_cap]");
+  GSB_CUDA(cudaSetDevice(ctx->device));
+  gsb_picard_params p{};
+  p.mu0 = 1.0;
+  p.z_min = z_min;
+  p.r_min = ctx->r_row.front();
+  p.r_max = ctx->r_row.back();
+  if (ctx->picard) {  // keep cached tables unless z_min changed
+    p.mu0 = std::isnan(ctx->picard->mu0) ? 1.0 : ctx->picard->mu0;
+    p.r_min = std::isnan(ctx->picard->r_min) ? p.r_min : ctx->picard->r_min;
+    p.r_max = std::isnan(ctx->picard->r_max) ? p.r_max : ctx->picard->r_max;
+  }
+  int rc = picard_ws_ensure(ctx, &p);
+  if (rc) return rc;
+  gsb_picard_ws *w = ctx->picard;
+  cudaStream_t st = (cudaStream_t)stream;
+  Bufs bufs{{const_cast<double *>(psi_dev), nullptr, nullptr}};
+  const int P = partials_for(ctx->nz, ctx->nr);
+  const GradGeom gg = make_grad_geom(ctx->dz, ctx->dr);
+  k_topo<<<dim3(P, batch), 256, 0, st>>>(bufs, nullptr, ctx->n, ctx->nz, ctx->nr, gg, w->rowmask, w->tpart, nullptr);
+  GSB_LAUNCH_CHECK();
+  if (saddle) {
+    volatile double dr2 = ctx->dr * ctx->dr, dz2 = ctx->dz * ctx->dz, f1 = 4.0 * ctx->dr, f2 = f1 * ctx->dz;
+    k_xpoint_saddle<<<batch, 256, 0, st>>>(bufs, nullptr, ctx->n, ctx->nz, ctx->nr, gg, dr2, dz2, f2, w->rowmask, w->s.xsel, nullptr);
+    GSB_LAUNCH_CHECK();
+  }
+  k_topo_final<<<(batch + 127) / 128, 128, 0, st>>>(bufs, nullptr, ctx->n, ctx->nr, P, w->tpart,
+                                                    saddle ? w->s.xsel : nullptr, out_dev, nullptr, 0, batch, nullptr);
+  GSB_LAUNCH_CHECK();
+  return GSB_OK;
+}
+
+int gsb_plasma_source(gsb_ctx *ctx, const double *psi_dev, const double *axis_bnd_dev,
+                      const double *ip_dev, double mu0, const gsb_profile *prof,
+                      const double *prof_dev, double *jphi_dev, int batch, void *stream) {
+  GSB_REQUIRE(ctx && psi_dev && axis_bnd_dev && ip_dev && prof && jphi_dev, "gsb_plasma_source: NULL argument");
+  GSB_REQUIRE(batch >= 1 && batch <= ctx->batch_cap, "gsb_plasma_source: batch outside [1, batch_cap]");
+  GSB_CUDA(cudaSetDevice(ctx->device));
+  gsb_picard_params p{};
+  p.mu0 = mu0;
+  p.z_min = ctx->z_axis.empty() ? 0.0 : ctx->z_axis.front();
+  p.r_min = ctx->r_row.front();
+  p.r_max = ctx->r_row.back();
+  if (ctx->picard && !std::isnan(ctx->picard->z_min)) {
+    p.z_min = ctx->picard->z_min;
+    p.r_min = ctx->picard->r_min;
+    p.r_max = ctx->picard->r_max;
+  }
+  int rc = picard_ws_ensure(ctx, &p);
+  if (rc) return rc;
+  gsb_picard_ws *w = ctx->picard;
+  cudaStream_t st = (cudaStream_t)stream;
+  Bufs bufs{{const_cast<double *>(psi_dev), nullptr, nullptr}};
+  const int P = partials_for(ctx->nz, ctx->nr);
+  k_source_raw<<<dim3(P, batch), 256, 0, st>>>(bufs, nullptr, ctx->n, ctx->nz, ctx->nr, axis_bnd_dev, to_dev(*prof),
+                                               prof_dev, ctx->r_dev, w->cf, jphi_dev, w->spart, nullptr);
+  GSB_LAUNCH_CHECK();
+  k_source_scale<<<dim3(P, batch), 256, 0, st>>>(ctx->n, ctx->nz, ctx->nr, ctx->dr, ctx->dz, ip_dev, w->spart, P, w->mr,
+                                                 jphi_dev, nullptr, nullptr, nullptr);
+  GSB_LAUNCH_CHECK();
+  return GSB_OK;
+}
+
+int gsb_b_field(gsb_ctx *ctx, const double *psi_dev, double *br_dev, double *bz_dev, int batch, void *stream) {
+  GSB_REQUIRE(ctx && psi_dev && br_dev && bz_dev, "gsb_b_field: NULL argument");
+  GSB_REQUIRE(batch >= 1 && batch <= 65535, "gsb_b_field: bad batch");
+  GSB_CUDA(cudaSetDevice(ctx->device));
+  const dim3 blk(32, 8, 1), grd((ctx->nr + 31) / 32, (ctx->nz + 7) / 8, batch);
+  k_bfield<<<grd, blk, 0, (cudaStream_t)stream>>>(psi_dev, ctx->nz, ctx->nr, make_grad_geom(ctx->dz, ctx->dr), ctx->r_dev, br_dev, bz_dev);
+  GSB_LAUNCH_CHECK();
+  return GSB_OK;
+}
+
+int gsb_picard_last_launched_iterations(gsb_ctx *ctx) { return ctx ? ctx->picard_last_iters : 0; }
+
+int gsb_picard_solve(gsb_ctx *ctx, const gsb_picard_params *p, double *psi_dev, const double *bc_dev,
+                     const double *ip_dev, const double *prof_dev, double *jphi_dev, double *summary_dev,
+                     double *hist_dev, double *gs_hist_dev, int batch, void *stream) {
+  GSB_REQUIRE(ctx && p && psi_dev && bc_dev && ip_dev && jphi_dev && summary_dev, "gsb_picard_solve: NULL argument");
+  GSB_REQUIRE(batch >= 1 && batch <= ctx->batch_cap, "gsb_picard_solve: batch outside [1, batch_cap]");
+  GSB_REQUIRE(p->max_iterations >= 1, "gsb_picard_solve: max_iterations must be >= 1");
+  GSB_REQUIRE(p->method >= 0 && p->method <= 2, "gsb_picard_solve: unknown method");
+  GSB_REQUIRE(std::isfinite(p->omega) && p->omega >= 1.0 && p->omega < 2.0,
+              "omega must be finite and satisfy 1.0 <= omega < 2.0");
+  GSB_REQUIRE(!p->require_gs_residual || p->gs_tol > 0.0, "solver.gs_residual_threshold must be > 0");
+  GSB_CUDA(cudaSetDevice(ctx->device));
+  int rc = ensure_plan(ctx, 5);
+  if (rc) return rc;
+  rc = picard_ws_ensure(ctx, p);
+  if (rc) return rc;
+  gsb_picard_ws *w = ctx->picard;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nz = ctx->nz, nr = ctx->nr;
+  const size_t n = ctx->n;
+  const LevelGeom &g = ctx->levels[0].g;
+  Bufs bufs{{psi_dev, w->buf1, w->buf2}};
+  PicardState &s = w->s;
+  const int P = partials_for(nz, nr);
+  const GradGeom gg = make_grad_geom(ctx->dz, ctx->dr);
+  const int rs = ring_size(nz, nr);
+  const int copy_blocks = (int)std::min<size_t>((n + 255) / 256, 64);
+  const ProfileDev prof = to_dev(p->prof);
+
+  k_picard_init<<<(batch + 127) / 128, 128, 0, st>>>(s, batch, p->seed ? 2 : 0, ip_dev, p->seed);
+  GSB_LAUNCH_CHECK();
+  rc = ring_save_launch(bc_dev, n, w->ring, nz, nr, batch, st);
+  if (rc) return rc;
+  if (p->seed) {
+    // Psi_best = Psi.copy() is taken BEFORE seeding (newton_solver.py:484,496)
+    GSB_CUDA(cudaMemcpyAsync(w->buf2, psi_dev, (size_t)batch * n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    volatile double ssum = w->seed_sum * ctx->dr;
+    volatile double ssum2 = ssum * ctx->dz;
+    k_seed_source<<<dim3(copy_blocks, batch), 256, 0, st>>>(n, nr, w->seedJ, ssum2, ip_dev, w->mr, jphi_dev, w->source, s.seed_active);
+    GSB_LAUNCH_CHECK();
+    for (int it = 0; it < 25; ++it) {  // 50 Jacobi steps, ping-pong psi <-> W
+      rc = jacobi_launch(g, psi_dev, w->source, w->W, batch, s.seed_active, st);
+      if (rc) return rc;
+      rc = jacobi_launch(g, w->W, w->source, psi_dev, batch, s.seed_active, st);
+      if (rc) return rc;
+    }
+  }
+
+  const double oma = 1.0 - p->alpha;
+  const int check_every = p->check_every > 0 ? p->check_every : 8;
+  volatile double dr2 = ctx->dr * ctx->dr, dz2 = ctx->dz * ctx->dz, f1 = 4.0 * ctx->dr, f2 = f1 * ctx->dz;
+  int k = 0;
+  for (; k < p->max_iterations; ++k) {
+    k_topo<<<dim3(P, batch), 256, 0, st>>>(bufs, s.cur, n, nz, nr, gg, w->rowmask, w->tpart, s.active);
+    GSB_LAUNCH_CHECK();
+    if (p->saddle) {
+      k_xpoint_saddle<<<batch, 256, 0, st>>>(bufs, s.cur, n, nz, nr, gg, dr2, dz2, f2, w->rowmask, s.xsel, s.active);
+      GSB_LAUNCH_CHECK();
+    }
+    k_topo_final<<<(batch + 127) / 128, 128, 0, st>>>(bufs, s.cur, n, nr, P, w->tpart, p->saddle ? s.xsel : nullptr,
+                                                      s.topo, s.axbnd, 1, batch, s.active);
+    GSB_LAUNCH_CHECK();
+    k_source_raw<<<dim3(P, batch), 256, 0, st>>>(bufs, s.cur, n, nz, nr, s.axbnd, prof, prof_dev, ctx->r_dev, w->cf,
+                                                 jphi_dev, w->spart, s.active);
+    GSB_LAUNCH_CHECK();
+    k_source_scale<<<dim3(P, batch), 256, 0, st>>>(n, nz, nr, ctx->dr, ctx->dz, ip_dev, w->spart, P, w->mr, jphi_dev,
+                                                   w->source, s.scale, s.active);
+    GSB_LAUNCH_CHECK();
+    if (p->method == 0) {
+      k_copy_from_cur<<<dim3(copy_blocks, batch), 256, 0, st>>>(bufs, s.cur, n, w->W, 0, s.active);
+      GSB_LAUNCH_CHECK();
+      rc = vcycle_launch(ctx, w->W, n, w->source, batch, p->omega, 3, 3, s.active, st);
+      if (rc) return rc;
+    } else if (p->method == 1) {
+      k_copy_from_cur<<<dim3(copy_blocks, batch), 256, 0, st>>>(bufs, s.cur, n, w->W, 1, s.active);
+      GSB_LAUNCH_CHECK();
+      rc = smooth_launch(g, w->W, n, w->source, n, batch, p->omega, 1, 1, s.active, st);
+      if (rc) return rc;
+    } else {
+      const dim3 blk(32, 8, 1), grd((nr + 31) / 32, (nz + 7) / 8, batch);
+      k_jacobi_from_cur<<<grd, blk, 0, st>>>(g, bufs, s.cur, w->source, w->W, s.active);
+      GSB_LAUNCH_CHECK();
+    }
+    k_relax<<<dim3(P, batch), 256, 0, st>>>(g, bufs, s.cur, s.nxt, w->W, w->ring, w->source, p->alpha, oma, w->rpart, s.active);
+    GSB_LAUNCH_CHECK();
+    const bool poll = ((k + 1) % check_every == 0) || (k + 1 == p->max_iterations);
+    if (poll) GSB_CUDA(cudaMemsetAsync(ctx->counter, 0, sizeof(int), st));
+    k_decide<<<(batch + 127) / 128, 128, 0, st>>>(s, w->rpart, P, (double)n, (double)(nz - 2) * (double)(nr - 2), p->tol,
+                                                  p->require_gs_residual, p->gs_tol, p->max_iterations, hist_dev,
+                                                  gs_hist_dev, ctx->counter, batch);
+    GSB_LAUNCH_CHECK();
+    if (poll) {
+      GSB_CUDA(cudaMemcpyAsync(ctx->h_counter, ctx->counter, sizeof(int), cudaMemcpyDeviceToHost, st));
+      GSB_CUDA(cudaStreamSynchronize(st));
+      if (ctx->h_counter[0] == 0) {
+        ++k;
+        break;
+      }
+    }
+  }
+  ctx->picard_last_iters = k;
+  k_finalize<<<dim3(copy_blocks, batch), 256, 0, st>>>(bufs, s, n, summary_dev, batch);
+  GSB_LAUNCH_CHECK();
+  return GSB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,95 @@
+"""GPU-tier providers for the reference's kernel registry.
+
+The reference dispatches ``gs_rb_sor_smooth`` and ``multigrid_solve`` through
+``scpn_fusion.core._multi_compat`` (``register_kernel(name, tier, fn)``, ``_multi_compat.py:240``)
+and ``benchmarks/bench_gpu_gs_solver.py`` calls ``providers._gpu_gs_rb_sor_smooth`` by name.
+These callables have the reference providers' signatures
+(``_multi_compat_providers.py:322-344,723-792``) but run in FP64 on the B200, so the
+cross-tier agreement is no longer f32-bounded.
+
+``PyGpuSolver`` / ``py_gpu_available`` / ``py_gpu_info`` reproduce the surface of the
+reference's PyO3 module ``scpn_fusion_rs`` (``fusion-python/src/bindings/gpu.rs:19-90``) so an
+UNMODIFIED ``bench_gpu_gs_solver.py`` can be pointed at this package.
+"""
+from __future__ import annotations
+
+from typing import Any
+
+import numpy as np
+
+from . import _device as D
+from . import _lib
+from . import multigrid_solve as _mg
+
+
+def _gpu_gs_rb_sor_smooth(psi: Any, source: Any, r_left: float, r_right: float, z_bottom: float, z_top: float, *,
+                          omega: float = 1.3, n_sweeps: int = 50) -> Any:
+    """``gs_rb_sor_smooth`` GPU tier: n_sweeps RB-SOR sweeps on a copy of *psi*, float64 out.
+
+    Geometry exactly as the NumPy tier builds it (``_multi_compat_providers.py:744-751``):
+    r_grid from ``linspace`` but ``dr = (r_right - r_left)/(nr - 1)``.
+    """
+    psi_arr = np.array(psi, dtype=np.float64, copy=True)
+    source_arr = np.asarray(source, dtype=np.float64)
+    nz, nr = psi_arr.shape
+    r_axis = np.linspace(r_left, r_right, nr)
+    dr = (r_right - r_left) / (nr - 1)
+    dz = (z_top - z_bottom) / (nz - 1)
+    return _mg.mg_smooth(psi_arr, source_arr, r_axis, dr, dz, omega, n_sweeps)
+
+
+def _gpu_multigrid_solve(source: Any, psi_bc: Any, r_min: float, r_max: float, z_min: float, z_max: float,
+                         nr: int, nz: int, *, tol: float = 1e-6, max_cycles: int = 500) -> Any:
+    """``multigrid_solve`` GPU tier (``_multi_compat_providers.py:322-344``)."""
+    return _mg.multigrid_solve(source, psi_bc, r_min, r_max, z_min, z_max, nr, nz, tol=tol, max_cycles=max_cycles)
+
+
+def _gpu_equilibrium_kernel_loader():
+    """Class loader for ``register_kernel_class("equilibrium_kernel", GPU, loader)``."""
+    from .fusion_kernel import FusionKernel
+
+    return FusionKernel
+
+
+def py_gpu_available() -> bool:
+    """``scpn_fusion_rs.py_gpu_available`` analogue: True when libgsb200 sees a CUDA device."""
+    try:
+        return _lib.load().gsb_device_count() > 0
+    except Exception:
+        return False
+
+
+def py_gpu_info() -> str:
+    torch = D.torch_mod()
+    if not py_gpu_available() or not torch.cuda.is_available():
+        return "none"
+    p = torch.cuda.get_device_properties(torch.cuda.current_device())
+    return f"{p.name} (sm_{p.major}{p.minor}, {p.total_memory // 2**20} MiB, libgsb200 FP64)"
+
+
+class PyGpuSolver:
+    """Surface of the reference's PyO3 ``PyGpuSolver`` (``bindings/gpu.rs:19-81``).
+
+    ``solve(psi, source, iterations, omega)`` takes flat sequences and returns a flat float32
+    array like the wgpu tier, but the sweeps themselves run in FP64.
+    """
+
+    def __init__(self, nr: int, nz: int, r_left: float, r_right: float, z_bottom: float, z_top: float):
+        if nr < 3 or nz < 3:
+            raise ValueError("grid must be at least 3x3")
+        self.nr, self.nz = int(nr), int(nz)
+        self.box = (float(r_left), float(r_right), float(z_bottom), float(z_top))
+
+    def solve(self, psi, source, iterations: int, omega: float):
+        p = np.asarray(psi, dtype=np.float64).reshape(self.nz, self.nr)
+        s = np.asarray(source, dtype=np.float64).reshape(self.nz, self.nr)
+        out = _gpu_gs_rb_sor_smooth(p, s, *self.box, omega=omega, n_sweeps=int(iterations))
+        return out.astype(np.float32).ravel()
+
+
+def register(multi: Any) -> None:
+    """Register the GPU tier into the reference's registry module (``_multi_compat``)."""
+    tier = multi.BackendTier.GPU
+    multi.register_kernel("gs_rb_sor_smooth", tier, _gpu_gs_rb_sor_smooth)
+    multi.register_kernel("multigrid_solve", tier, _gpu_multigrid_solve)
+    multi.register_kernel_class("equilibrium_kernel", tier, _gpu_equilibrium_kernel_loader)

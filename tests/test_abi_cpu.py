@@ -1,0 +1,137 @@
+"""CPU-only checks of the C ABI and the host logic (no compute calls without a GPU)."""
+from __future__ import annotations
+
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import gs_oracle as G
+from conftest import ROOT
+from scpn_fusion_core_b200 import _lib
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "gsb200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    names = re.findall(r"\b([a-z_][a-z0-9_]*)\s*\(", text)
+    return sorted({n for n in names if n.startswith("gsb_") or n in (
+        "create_solver", "set_boundary_dirichlet", "run_step", "run_step_converged", "destroy_solver",
+        "delete_solver")})
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = _lib.load()
+    declared = _declared_symbols()
+    assert len(declared) >= 30
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/gsb200.h but not exported"
+    assert set(declared) == set(_lib.SIGNATURES), "ctypes signature table out of sync with the header"
+    assert lib.gsb_abi_version() == 1
+
+
+def test_reference_abi_symbols_match_hpc_bridge_contract():
+    """The six names hpc_bridge.py:190-250 binds (destroy_solver or delete_solver accepted)."""
+    lib = _lib.load()
+    for name in ("create_solver", "run_step", "destroy_solver", "delete_solver", "set_boundary_dirichlet",
+                 "run_step_converged"):
+        assert hasattr(lib, name)
+    # invalid geometry -> NULL, like solver.cpp:209-210
+    assert lib.create_solver(1, 10, 1.0, 2.0, 0.0, 1.0) is None
+    assert lib.create_solver(10, 10, 2.0, 1.0, 0.0, 1.0) is None
+    # NULL handle / bad input are silent no-ops or 0 (solver.cpp:249-257,282-296)
+    lib.set_boundary_dirichlet(None, 1.0)
+    lib.run_step(None, None, None, 0, 1)
+    d = ctypes.c_double(5.0)
+    assert lib.run_step_converged(None, None, None, 0, 1, 1.5, 1e-6, ctypes.byref(d)) == 0
+    assert d.value == 0.0
+    lib.destroy_solver(None)
+
+
+@pytest.mark.parametrize("shape,expect", [
+    ((129, 129), [129, 65, 33, 17, 9, 5]), ((128, 128), [128, 64, 32, 16, 8, 4]),
+    ((257, 257), [257, 129, 65, 33, 17, 9, 5]), ((5, 5), [5]), ((4, 9), [4])])
+def test_plan_levels(shape, expect):
+    lib = _lib.load()
+    nz = (ctypes.c_int * 32)()
+    nr = (ctypes.c_int * 32)()
+    n = lib.gsb_plan_levels(shape[0], shape[1], 5, nz, nr, 32)
+    assert list(nz)[:n] == expect
+
+
+def test_level_tables_bit_exact_vs_oracle():
+    """Per-level R rows and a_e/a_w columns equal the oracle's restricted meshgrid coefficients."""
+    lib = _lib.load()
+    dp = ctypes.POINTER(ctypes.c_double)
+    for nz, nr, rmin, rmax in [(129, 129, 2.0, 10.0), (128, 128, 2.0, 10.0), (48, 80, 0.8, 2.6), (33, 41, 1.2, 2.2)]:
+        R = np.linspace(rmin, rmax, nr)
+        Z = np.linspace(-4, 4, nz)
+        dr, dz = float(R[1] - R[0]), float(Z[1] - Z[0])
+        rg, _ = np.meshgrid(R, Z)
+        lev = 0
+        while True:
+            r, ae, aw, sc = np.zeros(nr), np.zeros(nr), np.zeros(nr), np.zeros(4)
+            n = lib.gsb_plan_level_tables(nz, nr, R.ctypes.data_as(dp), dr, dz, 5, lev, r.ctypes.data_as(dp),
+                                          ae.ctypes.data_as(dp), aw.ctypes.data_as(dp), sc.ctypes.data_as(dp))
+            assert n == rg.shape[1]
+            a_e, a_w, a_ns, a_c = G._stencil_coeffs(rg, dr * 2.0 ** lev, dz * 2.0 ** lev)
+            np.testing.assert_array_equal(r[1:n - 1], rg[1, 1:-1])
+            np.testing.assert_array_equal(ae[1:n - 1], a_e[0])
+            np.testing.assert_array_equal(aw[1:n - 1], a_w[0])
+            assert (sc[2], sc[3]) == (a_ns, a_c)
+            if 5 >= rg.shape[0] or 5 >= rg.shape[1]:
+                break
+            rg = G.restrict_full_weight(rg)
+            lev += 1
+
+
+def test_no_gpu_means_loud_failure(has_cuda):
+    """Without a CUDA device the product path must fail loudly (no CPU fallback)."""
+    if has_cuda:
+        pytest.skip("a GPU is present")
+    lib = _lib.load()
+    assert lib.gsb_device_count() == 0
+    assert lib.create_solver(16, 16, 1.0, 2.0, -1.0, 1.0) is None
+    h = ctypes.c_void_p()
+    r = np.linspace(1, 2, 16)
+    rc = lib.gsb_create(ctypes.byref(h), 16, 16, r.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), None, 0.1, 0.1, 1, 0)
+    assert rc == _lib.GSB_ENODEV
+    assert "no usable CUDA device" in _lib.last_error()
+    import scpn_fusion_core_b200 as pkg
+    with pytest.raises(_lib.GsbError):
+        pkg.mg_smooth(np.zeros((9, 9)), np.zeros((9, 9)), np.ones((9, 9)), 0.1, 0.1, 1.0, 1)
+    with pytest.raises(_lib.GsbError):
+        pkg.FusionKernel({"dimensions": {"R_min": 1, "R_max": 2, "Z_min": -1, "Z_max": 1}})
+
+
+def test_product_does_not_import_the_oracle():
+    """Nothing under scpn_fusion_core_b200/ may reference oracle/ (SURVEY 8c rule)."""
+    pkg = os.path.join(ROOT, "scpn_fusion_core_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f), encoding="utf-8").read()
+                assert "gs_oracle" not in text and "oracle/" not in text, f
+
+
+def test_config_validation_matches_reference_schema():
+    from scpn_fusion_core_b200 import validate_config
+
+    base = {"dimensions": {"R_min": 2.0, "R_max": 10.0, "Z_min": -4.0, "Z_max": 4.0}}
+    cfg = validate_config(base)
+    assert cfg["grid_resolution"] == [129, 129]
+    assert cfg["solver"] == {"max_iterations": 1000, "convergence_threshold": 1e-4, "relaxation_factor": 0.1}
+    assert cfg["physics"]["vacuum_permeability"] == 1.25663706e-6
+    for bad in (
+        {"dimensions": {"R_min": 2.0, "R_max": 1.0, "Z_min": -4.0, "Z_max": 4.0}},
+        {"dimensions": {"R_min": -1.0, "R_max": 1.0, "Z_min": -4.0, "Z_max": 4.0}},
+        {**base, "grid_resolution": [3, 129]},
+        {**base, "solver": {"relaxation_factor": 1.5}},
+        {**base, "solver": {"max_iterations": 0}},
+        {**base, "coils": [{"r": -1.0, "z": 0.0}]},
+        {},
+    ):
+        with pytest.raises(ValueError):
+            validate_config(bad)
