@@ -25,7 +25,7 @@ import numpy as np
 
 from . import _device as D
 from . import _lib
-from . import multigrid_solve as _mg
+_mg = __import__("importlib").import_module(__package__ + ".multigrid_solve")  # package re-exports a same-named function
 
 logger = logging.getLogger(__name__)
 

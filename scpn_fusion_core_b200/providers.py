@@ -19,7 +19,9 @@ import numpy as np
 
 from . import _device as D
 from . import _lib
-from . import multigrid_solve as _mg
+import importlib
+
+_mg = importlib.import_module(__package__ + ".multigrid_solve")  # the package re-exports a same-named function
 
 
 def _gpu_gs_rb_sor_smooth(psi: Any, source: Any, r_left: float, r_right: float, z_bottom: float, z_top: float, *,
