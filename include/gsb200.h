@@ -71,6 +71,11 @@ int gsb_device_count(void);
 /* Count of kernels launched by this library in this process (bench.py's gpu_launches). */
 long long gsb_launch_count(void);
 
+/* Debug: clock64() totals per V-cycle phase of CTA 0 of the shared-memory-resident kernel
+ * (index 4*level + {0 pre-smooth, 1 residual+restrict, 2 prolong, 3 post-smooth}; the base level
+ * uses slot 0).  All zeros unless the library was built with -DGSB_PHASE_TIMING. out64: 64 values. */
+int gsb_debug_phase_cycles(long long *out64, int reset);
+
 /* Host-only planning helper (works without a GPU): level sizes of the V-cycle
  * the reference would run on (nz,nr) with `min_grid` (multigrid_solve.py:292,
  * coarse size (n+1)//2).  Writes up to `cap` (nz,nr) pairs, returns the number of

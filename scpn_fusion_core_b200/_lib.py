@@ -49,6 +49,7 @@ SIGNATURES = {
     "gsb_last_error": (c_char_p, []),
     "gsb_device_count": (c_int, []),
     "gsb_launch_count": (c_longlong, []),
+    "gsb_debug_phase_cycles": (c_int, [POINTER(c_longlong), c_int]),
     "gsb_plan_levels": (c_int, [c_int, c_int, c_int, _ip, _ip, c_int]),
     "gsb_plan_level_tables": (c_int, [c_int, c_int, _dp, c_double, c_double, c_int, c_int, _dp, _dp, _dp, _dp]),
     "gsb_create": (c_int, [POINTER(c_void_p), c_int, c_int, _dp, _dp, c_double, c_double, c_int, c_int]),

@@ -1,5 +1,6 @@
 // gsb_core.cu - context, level planning (host), error plumbing.
 #include "gsb_internal.cuh"
+#include "gsb_resident.cuh"
 
 #include <cstring>
 #include <mutex>
@@ -141,13 +142,28 @@ int ensure_plan(gsb_ctx *ctx, int min_grid) {
     g.r_safe = D.tables + 2 * nr;
     g.inv_r_safe = D.tables + 3 * nr;
     if (i > 0) {
-      const size_t bytes = (size_t)ctx->batch_cap * H.nz * H.nr * sizeof(double);
+      const size_t bytes = (size_t)ctx->batch_cap * 2 * H.nz * ((H.nr + 1) / 2) * sizeof(double);
       GSB_CUDA(cudaMalloc(&D.d, bytes));
       GSB_CUDA(cudaMalloc(&D.e, bytes));
     }
     ctx->levels.push_back(D);
   }
   ctx->planned_min_grid = min_grid;
+  // first level from which the whole V-cycle tail fits one SM's shared memory
+  const char *env = getenv("GSB_NO_RESIDENT");
+  ctx->res_l0 = (int)ctx->levels.size();
+  if (!(env && env[0] == '1')) {
+    RPlan plan;
+    for (int l0 = 0; l0 < (int)ctx->levels.size(); ++l0)
+      if (build_rplan(ctx, l0, 0, &plan)) {
+        ctx->res_l0 = l0;
+        break;
+      }
+  }
+  if (ctx->res_l0 == 0 && !ctx->split_src) {
+    const size_t hw = (ctx->nr + 1) / 2;
+    GSB_CUDA(cudaMalloc(&ctx->split_src, (size_t)ctx->batch_cap * 2 * ctx->nz * hw * sizeof(double)));
+  }
   return GSB_OK;
 }
 
@@ -224,6 +240,7 @@ int gsb_create(gsb_ctx **out, int nz, int nr, const double *r_row, const double 
   GSB_CUDA(cudaSetDevice(device));
   gsb_ctx *ctx = new gsb_ctx();
   ctx->device = device;
+  cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device);
   ctx->nz = nz;
   ctx->nr = nr;
   ctx->n = (size_t)nz * nr;
@@ -271,6 +288,7 @@ void gsb_destroy(gsb_ctx *ctx) {
   if (ctx->active) cudaFree(ctx->active);
   if (ctx->counter) cudaFree(ctx->counter);
   if (ctx->mg_bc) cudaFree(ctx->mg_bc);
+  if (ctx->split_src) cudaFree(ctx->split_src);
   if (ctx->h_counter) cudaFreeHost(ctx->h_counter);
   delete ctx;
 }

@@ -4,6 +4,7 @@
 // not fit one SM's shared memory and as the general path.  One thread per updated point,
 // batch in gridDim.z.  Arithmetic keeps NumPy's operand order (bit-identical results).
 #include "gsb_internal.cuh"
+#include "gsb_resident.cuh"
 
 namespace gsb {
 
@@ -198,13 +199,6 @@ int residual_norms_launch(gsb_ctx *ctx, const LevelGeom &g, const double *psi, s
 // ------------------------------------------------------------------------------------------
 // a6  full-weighting restriction (multigrid_solve.py:57-99), generic shapes
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ double fw9(double c, double s, double n, double w, double e, double sw,
-                                      double se, double nw, double ne) {
-  const double t2 = dmul(2.0, dadd(dadd(dadd(s, n), w), e));
-  const double t1 = dadd(dadd(dadd(sw, se), nw), ne);
-  return dmul(dadd(dadd(dmul(4.0, c), t2), t1), 0.0625);  // /16 is exact scaling
-}
-
 __global__ void __launch_bounds__(256)
 k_restrict(const double *__restrict__ fine, double *__restrict__ coarse, int nzf, int nrf, int nzc,
            int nrc) {
@@ -234,7 +228,7 @@ k_restrict(const double *__restrict__ fine, double *__restrict__ coarse, int nzf
 __global__ void __launch_bounds__(256)
 k_residual_restrict(LevelGeom g, const double *__restrict__ psi, size_t pstride,
                     const double *__restrict__ src, size_t sstride, double *__restrict__ dc, int nzc,
-                    int nrc, const int *__restrict__ active) {
+                    int nrc, int split_out, const int *__restrict__ active) {
   const int b = blockIdx.z;
   if (active && !active[b]) return;
   const int J = blockIdx.x * blockDim.x + threadIdx.x;
@@ -257,7 +251,12 @@ k_residual_restrict(LevelGeom g, const double *__restrict__ psi, size_t pstride,
       }
     v = fw9(d[1][1], d[0][1], d[2][1], d[1][0], d[1][2], d[0][0], d[0][2], d[2][0], d[2][2]);
   }
-  dc[((size_t)b * nzc + I) * nrc + J] = v;
+  if (split_out) {  // colour-split layout consumed by the resident kernel (gsb_resident.cuh)
+    const int hwc = (nrc + 1) / 2;
+    dc[(size_t)b * 2 * nzc * hwc + ((((I + J) & 1) * nzc + I) * hwc + (J >> 1))] = v;
+  } else {
+    dc[((size_t)b * nzc + I) * nrc + J] = v;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -377,33 +376,160 @@ static int base_solve_launch(const LevelGeom &g, double *x, size_t xstride, cons
 }
 
 // ------------------------------------------------------------------------------------------
-// a8  V-cycle driver (multigrid_solve.py:252-335), recursion unrolled over the planned levels
+// shared-memory-resident V-cycle tail: one CTA per equilibrium (gsb_resident.cuh)
+// ------------------------------------------------------------------------------------------
+bool build_rplan(const gsb_ctx *ctx, int l0, int extra_doubles, RPlan *out) {
+  const int L = (int)ctx->levels.size();
+  if (l0 < 0 || l0 >= L || L - l0 > kResMaxLevels) return false;
+  int off = 0;
+  out->nlev = L - l0;
+  for (int l = l0; l < L; ++l) {
+    RLevel &r = out->lev[l - l0];
+    const LevelGeom &g = ctx->levels[l].g;
+    r.nz = g.nz;
+    r.nr = g.nr;
+    r.hw = (g.nr + 1) / 2;
+    r.nk = g.nr / 2;
+    r.g = g;
+    const int T = kResThreads;
+    const int rows = std::max(r.nz - 2, 0);
+    r.lk = 0;
+    while ((1 << r.lk) < r.nk) ++r.lk;
+    r.nch = std::max(1, std::min(rows, T >> r.lk));
+    r.rpc = rows > 0 ? (rows + r.nch - 1) / r.nch : 0;
+    if (r.rpc > 1 && (r.rpc & 1)) {  // even chunks keep the row-parity pattern uniform across a warp
+      r.rpc += 1;
+      r.nch = (rows + r.rpc - 1) / r.rpc;
+    }
+    const int ncj = std::max(r.nr - 2, 1);
+    r.lj = 0;
+    while ((1 << r.lj) < ncj) ++r.lj;
+    r.cch = std::max(1, std::min(rows, T >> r.lj));
+    r.crpc = rows > 0 ? (rows + r.cch - 1) / r.cch : 0;
+    const int planes = 2 * r.nz * r.hw;
+    r.x_off = off;
+    off += planes;
+    if (l > l0) {
+      r.d_off = off;
+      off += planes;
+    } else {
+      r.d_off = -1;
+    }
+  }
+  for (int l = l0; l < L; ++l) {  // column tables of the coarse levels live in shared memory too
+    RLevel &r = out->lev[l - l0];
+    r.t_off = -1;
+    if (l > l0) {
+      r.t_off = off;
+      off += 2 * r.nr;
+    }
+  }
+  out->pool_doubles = off;
+  return (size_t)(off + res_stage_doubles(out->nlev) + extra_doubles) * sizeof(double) <= (size_t)kResSmemMax;
+}
+
+// dense [nz][nr] -> colour-split [2][nz][hw]
+__global__ void __launch_bounds__(256)
+k_dense_to_split(const double *__restrict__ in, size_t istride, double *__restrict__ out, int nz, int nr,
+                 const int *__restrict__ active) {
+  const int b = blockIdx.y;
+  if (active && !active[b]) return;
+  const int hw = (nr + 1) / 2;
+  const double *f = in + (size_t)b * istride;
+  double *o = out + (size_t)b * 2 * nz * hw;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nz * nr; i += gridDim.x * blockDim.x) {
+    const int iz = i / nr, ir = i - iz * nr;
+    o[split_index(nz, hw, iz, ir)] = f[i];
+  }
+}
+
+// x: dense [b][nz][nr] (stride xstride) of the finest resident level; rhs: colour-split global.
+__global__ void __launch_bounds__(kResThreads, 1)
+k_vcycle_resident(const __grid_constant__ RPlan plan, double *__restrict__ x, size_t xstride, const double *__restrict__ rhs,
+                  int zero_init, int batch, double omega, int pre, int post,
+                  const int *__restrict__ active) {
+  const int lev_off = res_stage(plan);
+  const RLevel &F = res_level(lev_off, 0);
+  const int planes = 2 * F.nz * F.hw;
+  for (int b = blockIdx.x; b < batch; b += gridDim.x) {
+    if (active && !active[b]) continue;
+    double *xb = x + (size_t)b * xstride;
+    if (zero_init)
+      res_zero_off(F.x_off, planes);
+    else
+      res_load_dense(xb, F.x_off, F.nz, F.nr, F.hw);
+    __syncthreads();
+    res_vcycle(lev_off, plan.nlev, rhs + (size_t)b * planes, omega, pre, post);
+    __syncthreads();
+    res_store_dense(xb, F.x_off, F.nz, F.nr, F.hw);
+    __syncthreads();
+  }
+}
+
+static int resident_launch(gsb_ctx *ctx, int l0, double *x, size_t xstride, const double *rhs_split,
+                           int zero_init, int batch, double omega, int pre, int post, const int *active,
+                           cudaStream_t st) {
+  RPlan plan;
+  if (!build_rplan(ctx, l0, 0, &plan)) {
+    set_error("resident_launch: plan does not fit shared memory");
+    return GSB_EINVAL;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    GSB_CUDA(cudaFuncSetAttribute(k_vcycle_resident, cudaFuncAttributeMaxDynamicSharedMemorySize, kResSmemMax));
+    attr_set = true;
+  }
+  const size_t smem = (size_t)(plan.pool_doubles + res_stage_doubles(plan.nlev)) * sizeof(double);
+  const int grid = std::min(batch, ctx->num_sms);
+  k_vcycle_resident<<<grid, kResThreads, smem, st>>>(plan, x, xstride, rhs_split, zero_init, batch, omega, pre, post, active);
+  GSB_LAUNCH_CHECK();
+  return GSB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// a8  V-cycle driver (multigrid_solve.py:252-335), recursion unrolled over the planned levels.
+// Levels [0, res_l0) stream through HBM; levels [res_l0, L) run inside k_vcycle_resident.
 // ------------------------------------------------------------------------------------------
 int vcycle_launch(gsb_ctx *ctx, double *psi, size_t psi_stride, const double *src, int batch,
                   double omega, int pre, int post, const int *active, cudaStream_t st) {
   const int L = (int)ctx->levels.size();
+  const int l0 = ctx->res_l0;
   const dim3 blk(32, 8, 1);
   auto X = [&](int l) { return l == 0 ? psi : ctx->levels[l].e; };
   auto XS = [&](int l) { return l == 0 ? psi_stride : (size_t)ctx->levels[l].g.nz * ctx->levels[l].g.nr; };
   auto S = [&](int l) { return l == 0 ? src : (const double *)ctx->levels[l].d; };
   auto SS = [&](int l) { return l == 0 ? ctx->n : (size_t)ctx->levels[l].g.nz * ctx->levels[l].g.nr; };
-  for (int l = 0; l < L - 1; ++l) {
+  const int top = std::min(l0, L - 1);  // levels [0, top) are smoothed by streaming kernels
+  for (int l = 0; l < top; ++l) {
     const LevelGeom &g = ctx->levels[l].g;
     const LevelGeom &c = ctx->levels[l + 1].g;
     int rc = smooth_launch(g, X(l), XS(l), S(l), SS(l), batch, omega, pre, 0, active, st);
     if (rc) return rc;
     const dim3 grd((c.nr + 31) / 32, (c.nz + 7) / 8, batch);
-    k_residual_restrict<<<grd, blk, 0, st>>>(g, X(l), XS(l), S(l), SS(l), ctx->levels[l + 1].d, c.nz, c.nr, active);
+    const int split = (l + 1 == l0) ? 1 : 0;
+    k_residual_restrict<<<grd, blk, 0, st>>>(g, X(l), XS(l), S(l), SS(l), ctx->levels[l + 1].d, c.nz, c.nr, split, active);
     GSB_LAUNCH_CHECK();
-    if (l + 1 < L - 1)  // the base solve zero-initialises in shared memory
+    if (l + 1 < L - 1 && l + 1 != l0)  // resident / base solve zero-initialise on chip
       GSB_CUDA(cudaMemsetAsync(ctx->levels[l + 1].e, 0, (size_t)batch * c.nz * c.nr * sizeof(double), st));
   }
-  {
+  if (l0 < L) {
+    int rc;
+    if (l0 == 0) {
+      const LevelGeom &g = ctx->levels[0].g;
+      const int blocks = std::min((g.nz * g.nr + 255) / 256, 32);
+      k_dense_to_split<<<dim3(blocks, batch), 256, 0, st>>>(src, ctx->n, ctx->split_src, g.nz, g.nr, active);
+      GSB_LAUNCH_CHECK();
+      rc = resident_launch(ctx, 0, psi, psi_stride, ctx->split_src, 0, batch, omega, pre, post, active, st);
+    } else {
+      rc = resident_launch(ctx, l0, ctx->levels[l0].e, XS(l0), ctx->levels[l0].d, 1, batch, omega, pre, post, active, st);
+    }
+    if (rc) return rc;
+  } else {
     const LevelGeom &g = ctx->levels[L - 1].g;
     int rc = base_solve_launch(g, X(L - 1), XS(L - 1), S(L - 1), SS(L - 1), L > 1 ? 1 : 0, batch, omega, 50, active, st);
     if (rc) return rc;
   }
-  for (int l = L - 2; l >= 0; --l) {
+  for (int l = top - 1; l >= 0; --l) {
     const LevelGeom &g = ctx->levels[l].g;
     const LevelGeom &c = ctx->levels[l + 1].g;
     if (g.nz > 2 && g.nr > 2) {
@@ -480,6 +606,23 @@ using namespace gsb;
 static bool omega_ok(double w) { return std::isfinite(w) && w >= 1.0 && w < 2.0; }
 
 extern "C" {
+
+// debug: per-phase clock64 totals of CTA 0 of k_vcycle_resident (zeros unless built with
+// -DGSB_PHASE_TIMING); reset!=0 clears the counters after reading.
+int gsb_debug_phase_cycles(long long *out64, int reset) {
+#ifdef GSB_PHASE_TIMING
+  if (out64) GSB_CUDA(cudaMemcpyFromSymbol(out64, g_phase, 64 * sizeof(long long)));
+  if (reset) {
+    long long z[64] = {0};
+    GSB_CUDA(cudaMemcpyToSymbol(g_phase, z, sizeof(z)));
+  }
+#else
+  if (out64)
+    for (int i = 0; i < 64; ++i) out64[i] = 0;
+  (void)reset;
+#endif
+  return GSB_OK;
+}
 
 int gsb_smooth(gsb_ctx *ctx, double *psi_dev, const double *src_dev, int batch, double omega,
                int n_sweeps, int clip, void *stream) {
