@@ -11,6 +11,9 @@
 //   D   k_decide        history, best-state tracking, convergence, buffer rotation  (a13)
 // Per-equilibrium state lives in device arrays; the host only polls an active counter.
 #include "gsb_internal.cuh"
+#include "gsb_resident.cuh"
+
+#include <cstdlib>
 
 constexpr int kPT = 8;   // max partial blocks per equilibrium
 constexpr int kTW = 8;   // doubles per topo partial
@@ -39,6 +42,9 @@ struct gsb_picard_ws {
   // cached host-side parameters the device tables were built for
   double mu0 = NAN, z_min = NAN, r_min = NAN, r_max = NAN;
   double seed_sum = 0.0;
+  // private per-CTA workspace of the persistent resident solve: [grid][4*n + 2*nz*hw]
+  double *res_ws = nullptr;
+  int res_grid = 0;
 };
 
 namespace gsb {
@@ -556,6 +562,433 @@ k_bfield(const double *__restrict__ psi, int nz, int nr, GradGeom gg, const doub
   bz[b * n + (size_t)iz * nr + ir] = dmul(inv, gr);
 }
 
+
+// ============================================================================================
+// Persistent shared-memory-resident Picard solve: ONE CTA runs the COMPLETE solve of one
+// equilibrium (seed, every Picard iteration, V-cycles, convergence logic) and then fetches the
+// next one.  psi lives in the colour-split shared-memory planes (gsb_resident.cuh) for the whole
+// solve; the only per-iteration global traffic is the CTA's private, L2-resident workspace
+// (previous iterate, J, split right-hand side).  No host polling, no launch per phase, and an
+// equilibrium stops the moment it converges instead of waiting for the slowest of the batch.
+// ============================================================================================
+struct PicardResArgs {
+  double *psi;              // [B][n] in: initial flux, out: solution
+  const double *bc;         // [B][n] boundary map (wall ring read)
+  const double *ip;         // [B]
+  const double *prof_dev;   // NULL or [B][8]
+  double *jphi;             // [B][n] out
+  double *summary;          // [B][16] out
+  double *hist, *gs_hist;   // NULL or [B][max_iter]
+  double *ws_psi;           // [grid][3][n]   iterate rotation (cur / next / best)
+  double *ws_j;             // [grid][n]      J_raw -> J_phi
+  double *ws_src;           // [grid][2*nz*hw] right-hand side, colour-split
+  const double *seedJ, *cf, *mr, *rrow;
+  const int *rowmask;
+  double seed_sum_drdz;
+  int batch, max_iter, seed, saddle, need_gs;
+  double tol, gs_tol, alpha, oma, omega;
+  double dr, dz, dr2, dz2, four_drdz;
+  GradGeom gg;
+  ProfileDev prof;
+  int scratch_off;          // pool offset (doubles) of 96 doubles of reduction / broadcast scratch
+  int tplane_off;           // pool offset of a spare half plane (Jacobi seed)
+};
+
+__device__ __forceinline__ double pl(int xo, int nz, int hw, int iz, int ir) {
+  return res_pool[xo + split_index(nz, hw, iz, ir)];
+}
+
+// np.gradient on the resident planes (same arithmetic as grad_point)
+__device__ __forceinline__ void grad_planes(int xo, int nz, int nr, int hw, int iz, int ir, const GradGeom &gg,
+                                            double &gz, double &gr) {
+  const double c = pl(xo, nz, hw, iz, ir);
+  if (iz == 0)
+    gz = ddiv_y(dsub(pl(xo, nz, hw, 1, ir), c), gg.dz, gg.inv_dz);
+  else if (iz == nz - 1)
+    gz = ddiv_y(dsub(c, pl(xo, nz, hw, iz - 1, ir)), gg.dz, gg.inv_dz);
+  else
+    gz = ddiv_y(dsub(pl(xo, nz, hw, iz + 1, ir), pl(xo, nz, hw, iz - 1, ir)), gg.two_dz, gg.inv_two_dz);
+  if (ir == 0)
+    gr = ddiv_y(dsub(pl(xo, nz, hw, iz, 1), c), gg.dr, gg.inv_dr);
+  else if (ir == nr - 1)
+    gr = ddiv_y(dsub(c, pl(xo, nz, hw, iz, ir - 1)), gg.dr, gg.inv_dr);
+  else
+    gr = ddiv_y(dsub(pl(xo, nz, hw, iz, ir + 1), pl(xo, nz, hw, iz, ir - 1)), gg.two_dr, gg.inv_two_dr);
+}
+
+// block-wide broadcast of a value computed by thread 0 (through the scratch area)
+__device__ __forceinline__ double bcast_d(double v, int slot_off) {
+  __syncthreads();
+  if (threadIdx.x == 0) res_pool[slot_off] = v;
+  __syncthreads();
+  return res_pool[slot_off];
+}
+
+__global__ void __launch_bounds__(kResThreads, 1)
+k_picard_resident(const __grid_constant__ RPlan plan, const __grid_constant__ PicardResArgs a) {
+  const int lev_off = res_stage(plan);
+  const RLevel &F = res_level(lev_off, 0);
+  const int nz = F.nz, nr = F.nr, hw = F.hw, xo = F.x_off;
+  const int n = nz * nr, planes = 2 * nz * hw;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  double *sh = res_pool + a.scratch_off;            // 32 doubles reduction scratch
+  int *shi = reinterpret_cast<int *>(sh + 32);       // 32 ints (16 doubles)
+  const int bslot = a.scratch_off + 48;              // broadcast slots
+  double *wpsi = a.ws_psi + (size_t)blockIdx.x * 3 * n;
+  double *wj = a.ws_j + (size_t)blockIdx.x * n;
+  double *wsrc = a.ws_src + (size_t)blockIdx.x * planes;
+  const double n_all = (double)n, n_int = (double)(nz - 2) * (double)(nr - 2);
+
+  for (int b = blockIdx.x; b < a.batch; b += gridDim.x) {
+    const double *bc = a.bc + (size_t)b * n;
+    const double ipb = a.ip[b];
+    double pp[4], pf[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      pp[i] = a.prof_dev ? a.prof_dev[(size_t)b * 8 + i] : a.prof.p[i];
+      pf[i] = a.prof_dev ? a.prof_dev[(size_t)b * 8 + 4 + i] : a.prof.f[i];
+    }
+    // ---- initial flux -> planes; pre-seed copy is the initial "best" state (newton_solver.py:484)
+    __syncthreads();
+    res_load_dense(a.psi + (size_t)b * n, xo, nz, nr, hw);
+    int cur = 0, best = 0, nxt = 1;
+    const bool do_seed = a.seed && fabs(ipb) >= 1e-12;
+    if (a.seed) {
+      for (int i = threadIdx.x; i < n; i += blockDim.x) wpsi[2 * n + i] = a.psi[(size_t)b * n + i];
+      best = 2;
+    }
+    __syncthreads();
+
+    // ---- seed: Gaussian source scaled to Ip, 50 sanitised/clipped Jacobi steps (iterative_solver.py:384-410)
+    if (do_seed) {
+      const double sc = a.seed_sum_drdz > 0.0 ? __ddiv_rn(ipb, a.seed_sum_drdz) : 1.0;
+      for (int iz = warp; iz < nz; iz += nw)
+        for (int ir = lane; ir < nr; ir += 32) {
+          const double j = dmul(a.seedJ[iz * nr + ir], sc);
+          wj[iz * nr + ir] = j;
+          wsrc[split_index(nz, hw, iz, ir)] = dmul(a.mr[ir], j);
+        }
+      __syncthreads();
+      int p0 = xo, p1 = xo + nz * hw, pt = a.tplane_off;  // colour-0 plane, colour-1 plane, spare
+      const double *tab = F.g.a_e;
+      for (int step = 0; step < 50; ++step) {
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          // new colour-c values from the OLD other colour; colour 0 goes to the spare plane,
+          // colour 1 is then updated in place from the old colour-0 plane
+          const int src_plane = c == 0 ? p0 : p1;
+          const int oth_plane = c == 0 ? p1 : p0;
+          const int dst_plane = c == 0 ? pt : p1;
+          for (int iz = warp; iz < nz; iz += nw) {
+            const int s = (c + iz) & 1;
+            for (int k = lane; k < hw; k += 32) {
+              const int ir = 2 * k + s;
+              if (ir >= nr) continue;
+              const int o = iz * hw + k;
+              double v;
+              if (iz == 0 || iz == nz - 1 || ir == 0 || ir == nr - 1) {
+                v = sanitize(res_pool[src_plane + o]);
+              } else {
+                const double cc = sanitize(res_pool[oth_plane + o]);
+                const double side = sanitize(res_pool[oth_plane + o - 1 + 2 * s]);
+                const double S = sanitize(res_pool[oth_plane + o - hw]), N = sanitize(res_pool[oth_plane + o + hw]);
+                const double f = sanitize(wsrc[c * nz * hw + o]);
+                double acc = dadd(dmul(tab[ir], s ? side : cc), dmul(tab[nr + ir], s ? cc : side));
+                acc = dadd(acc, dmul(F.g.a_ns, S));
+                acc = dadd(acc, dmul(F.g.a_ns, N));
+                acc = dsub(acc, f);
+                v = clip_cap(ddiv_y(acc, F.g.a_c, F.g.inv_a_c));
+              }
+              res_pool[dst_plane + o] = v;
+            }
+          }
+          __syncthreads();
+        }
+        const int t = p0;  // the spare plane now holds colour 0
+        p0 = pt;
+        pt = t;
+      }
+      // 50 swaps: colour 0 is back in its home plane
+    }
+    // current iterate -> workspace slot `cur`
+    res_store_dense(wpsi + (size_t)cur * n, xo, nz, nr, hw);
+    __syncthreads();
+
+    int status = 0, iters = 0;
+    double diff_best = 1e9, gs_best = INFINITY, gs_last = INFINITY, diff_last = 0.0, scale = 0.0;
+    double psi_ax = 0.0, psi_b = 0.0, t_izax = 0, t_irax = 0, t_izx = 0, t_irx = 0, t_found = 0;
+
+    for (int k = 0; k < a.max_iter; ++k) {
+      // ---- T: topology on the resident planes (a10, a11)
+      ValIdx mx{0.0, -1}, mb{0.0, -1};
+      double mn = INFINITY;
+      for (int iz = warp; iz < nz; iz += nw) {
+        const bool div = a.rowmask[iz] != 0;
+        for (int ir = lane; ir < nr; ir += 32) {
+          const int flat = iz * nr + ir;
+          const double v = pl(xo, nz, hw, iz, ir);
+          mx = better<true>(mx, ValIdx{v, flat});
+          mn = fmin(mn, v);
+          if (div) {
+            double gz, gr;
+            grad_planes(xo, nz, nr, hw, iz, ir, a.gg, gz, gr);
+            const double bm = hypot_glibc(gr, gz);
+            if (isfinite(bm)) mb = better<false>(mb, ValIdx{bm, flat});
+          }
+        }
+      }
+      mx = block_arg<true>(mx, sh, shi);
+      __syncthreads();
+      mb = block_arg<false>(mb, sh, shi);
+      __syncthreads();
+      mn = -block_max(-mn, sh);
+      int xi = mb.i;  // valid in thread 0
+      if (a.saddle) {
+        // fusion_kernel.py:295-337: up to 16 smallest masked |grad psi|, keep Hessian saddles
+        double prev_v = -1.0, best_v = INFINITY;
+        int prev_i = -1, best_i = -1;
+        for (int round = 0; round < 16; ++round) {
+          ValIdx c{0.0, -1};
+          for (int iz = warp; iz < nz; iz += nw) {
+            if (!a.rowmask[iz]) continue;
+            for (int ir = lane; ir < nr; ir += 32) {
+              const int flat = iz * nr + ir;
+              double gz, gr;
+              grad_planes(xo, nz, nr, hw, iz, ir, a.gg, gz, gr);
+              const double bm = hypot_glibc(gr, gz);
+              if (!isfinite(bm)) continue;
+              if (bm < prev_v || (bm == prev_v && flat <= prev_i)) continue;
+              c = better<false>(c, ValIdx{bm, flat});
+            }
+          }
+          __syncthreads();
+          c = block_arg<false>(c, sh, shi);
+          // broadcast the pick
+          if (threadIdx.x == 0) {
+            res_pool[bslot] = c.v;
+            res_pool[bslot + 1] = (double)c.i;
+          }
+          __syncthreads();
+          prev_v = res_pool[bslot];
+          prev_i = (int)res_pool[bslot + 1];
+          __syncthreads();
+          if (prev_i < 0) break;
+          const int iz = prev_i / nr, ir = prev_i - iz * nr;
+          if (iz > 0 && iz < nz - 1 && ir > 0 && ir < nr - 1) {
+            const double q0 = pl(xo, nz, hw, iz, ir), c2 = dmul(2.0, q0);
+            const double d2r = __ddiv_rn(dadd(dsub(pl(xo, nz, hw, iz, ir + 1), c2), pl(xo, nz, hw, iz, ir - 1)), a.dr2);
+            const double d2z = __ddiv_rn(dadd(dsub(pl(xo, nz, hw, iz + 1, ir), c2), pl(xo, nz, hw, iz - 1, ir)), a.dz2);
+            const double drz = __ddiv_rn(dadd(dsub(dsub(pl(xo, nz, hw, iz + 1, ir + 1), pl(xo, nz, hw, iz + 1, ir - 1)),
+                                                   pl(xo, nz, hw, iz - 1, ir + 1)),
+                                              pl(xo, nz, hw, iz - 1, ir - 1)),
+                                         a.four_drdz);
+            const double det = dsub(dmul(d2r, d2z), dmul(drz, drz));
+            if (isfinite(det) && det < 0.0 && prev_v < best_v) {
+              best_v = prev_v;
+              best_i = prev_i;
+            }
+          }
+        }
+        if (best_i >= 0) xi = best_i;
+      }
+      // ---- TF: psi_axis / psi_boundary (thread 0), broadcast
+      if (threadIdx.x == 0) {
+        double pax = mx.v;
+        if (fabs(pax) < 1e-6) pax = 1e-6;
+        double px;
+        double fx = 0.0, izx = 0.0, irx = 0.0;
+        if (xi >= 0) {
+          const int iz = xi / nr, ir = xi - iz * nr;
+          px = pl(xo, nz, hw, iz, ir);
+          fx = 1.0;
+          izx = iz;
+          irx = ir;
+        } else {
+          px = mn;
+        }
+        double pb = px;
+        if (fabs(dsub(pax, pb)) < 0.1) pb = dmul(pax, 0.1);
+        res_pool[bslot] = pax;
+        res_pool[bslot + 1] = pb;
+        res_pool[bslot + 2] = (double)(mx.i / nr);
+        res_pool[bslot + 3] = (double)(mx.i % nr);
+        res_pool[bslot + 4] = izx;
+        res_pool[bslot + 5] = irx;
+        res_pool[bslot + 6] = fx;
+      }
+      __syncthreads();
+      psi_ax = res_pool[bslot];
+      psi_b = res_pool[bslot + 1];
+      t_izax = res_pool[bslot + 2];
+      t_irax = res_pool[bslot + 3];
+      t_izx = res_pool[bslot + 4];
+      t_irx = res_pool[bslot + 5];
+      t_found = res_pool[bslot + 6];
+      __syncthreads();
+
+      // ---- S1: J_raw(psi) + deterministic block sum (a12)
+      double denom = dsub(psi_b, psi_ax);
+      if (fabs(denom) < 1e-9) denom = 1e-9;
+      const double inv_denom = __ddiv_rn(1.0, denom);
+      double acc = 0.0;
+      for (int iz = warp; iz < nz; iz += nw)
+        for (int ir = lane; ir < nr; ir += 32) {
+          const double pn = ddiv_y(dsub(pl(xo, nz, hw, iz, ir), psi_ax), denom, inv_denom);
+          double pr = 0.0, ff = 0.0;
+          if (pn >= 0.0 && pn < 1.0) {
+            if (a.prof.hmode) {
+              pr = mtanh_dev(pn, pp);
+              ff = mtanh_dev(pn, pf);
+            } else {
+              pr = dsub(1.0, pn);
+              ff = pr;
+            }
+          }
+          const double j = dadd(dmul(0.5, dmul(a.rrow[ir], pr)), dmul(0.5, dmul(a.cf[ir], ff)));
+          wj[iz * nr + ir] = j;
+          acc += j;
+        }
+      acc = block_sum(acc, sh);
+      const double jsum = bcast_d(acc, bslot + 8);
+      // ---- S2: J = J_raw * Ip/I ; Source = (-mu0 R) J   (split layout)
+      const double icur = dmul(dmul(jsum, a.dr), a.dz);
+      const bool ok = fabs(icur) > 1e-9;
+      scale = ok ? __ddiv_rn(ipb, icur) : 0.0;
+      for (int iz = warp; iz < nz; iz += nw)
+        for (int ir = lane; ir < nr; ir += 32) {
+          const double j = ok ? dmul(wj[iz * nr + ir], scale) : 0.0;
+          wj[iz * nr + ir] = j;
+          wsrc[split_index(nz, hw, iz, ir)] = dmul(a.mr[ir], j);
+        }
+      __syncthreads();
+
+      // ---- E: one V-cycle on the planes (they hold a copy of the current iterate)
+      res_vcycle(lev_off, plan.nlev, wsrc, a.omega, 3, 3);
+      __syncthreads();
+
+      // ---- R: wall BC, NaN flag, mean|dpsi|, under-relaxation (in place), GS residual
+      const double *old = wpsi + (size_t)cur * n;
+      double *out = wpsi + (size_t)nxt * n;
+      double dsum = 0.0;
+      int bad = 0;
+      for (int iz = warp; iz < nz; iz += nw)
+        for (int ir = lane; ir < nr; ir += 32) {
+          const int o = iz * nr + ir;
+          const int so = xo + split_index(nz, hw, iz, ir);
+          const bool wall = iz == 0 || iz == nz - 1 || ir == 0 || ir == nr - 1;
+          const double wn = wall ? bc[o] : res_pool[so];
+          const double ov = old[o];
+          if (isnan(wn) || isinf(wn)) bad = 1;
+          dsum += fabs(dsub(wn, ov));
+          const double c = dadd(dmul(a.oma, ov), dmul(a.alpha, wn));
+          res_pool[so] = c;
+          out[o] = c;
+        }
+      const int anybad = __syncthreads_or(bad);
+      double rmax = 0.0, rsq = 0.0;
+      for (int iz = 1 + warp; iz < nz - 1; iz += nw)
+        for (int ir = 1 + lane; ir < nr - 1; ir += 32) {
+          const double r = dsub(gs_apply(F.g, ir, pl(xo, nz, hw, iz, ir), pl(xo, nz, hw, iz, ir + 1),
+                                         pl(xo, nz, hw, iz, ir - 1), pl(xo, nz, hw, iz - 1, ir),
+                                         pl(xo, nz, hw, iz + 1, ir)),
+                                wsrc[split_index(nz, hw, iz, ir)]);
+          const double ar = fabs(r);
+          if (ar > rmax) rmax = ar;
+          rsq += r * r;
+        }
+      dsum = block_sum(dsum, sh);
+      __syncthreads();
+      rmax = block_max(rmax, sh);
+      __syncthreads();
+      rsq = block_sum(rsq, sh);
+      // ---- D: decide (thread 0), broadcast
+      if (threadIdx.x == 0) {
+        double code = 0.0;  // 0 continue, 1 converged, 2 max-iter, 3 diverged
+        double dbest = diff_best, gbest = gs_best, dl = diff_last, gl = gs_last;
+        double improved = 0.0;
+        if (anybad) {
+          code = 3.0;
+        } else {
+          const double diff = dsum / n_all;
+          const double gs = (rmax > 0.0 && n_int > 0.0) ? sqrt(rsq / n_int) : 0.0;
+          if (a.hist) a.hist[(size_t)b * a.max_iter + k] = diff;
+          if (a.gs_hist) a.gs_hist[(size_t)b * a.max_iter + k] = gs;
+          dl = diff;
+          gl = gs;
+          if (gs < gbest) gbest = gs;
+          if (diff < dbest) {
+            dbest = diff;
+            improved = 1.0;
+          }
+          if (diff < a.tol && (!a.need_gs || gs < a.gs_tol))
+            code = 1.0;
+          else if (k + 1 >= a.max_iter)
+            code = 2.0;
+        }
+        res_pool[bslot] = code;
+        res_pool[bslot + 1] = dbest;
+        res_pool[bslot + 2] = gbest;
+        res_pool[bslot + 3] = dl;
+        res_pool[bslot + 4] = gl;
+        res_pool[bslot + 5] = improved;
+      }
+      __syncthreads();
+      const int code = (int)res_pool[bslot];
+      diff_best = res_pool[bslot + 1];
+      gs_best = res_pool[bslot + 2];
+      diff_last = res_pool[bslot + 3];
+      gs_last = res_pool[bslot + 4];
+      const bool improved = res_pool[bslot + 5] != 0.0;
+      __syncthreads();
+      iters = k + 1;
+      if (code == 3) {  // revert to the best state (newton_solver.py:518-532)
+        status = 3;
+        cur = best;
+        break;
+      }
+      const int newcur = nxt;
+      if (improved) best = newcur;
+      cur = newcur;
+      nxt = (cur == best) ? (cur + 1) % 3 : 3 - cur - best;
+      if (code != 0) {
+        status = code;
+        break;
+      }
+    }
+
+    // ---- results
+    {
+      const double *fin = wpsi + (size_t)cur * n;
+      double *po = a.psi + (size_t)b * n;
+      double *jo = a.jphi + (size_t)b * n;
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        po[i] = fin[i];
+        jo[i] = wj[i];
+      }
+      if (threadIdx.x == 0 && a.summary) {
+        double *o = a.summary + (size_t)b * 16;
+        o[0] = (double)iters;
+        o[1] = status == 1 ? 1.0 : 0.0;
+        o[2] = diff_best;
+        o[3] = gs_last;
+        o[4] = gs_best;
+        o[5] = (double)status;
+        o[6] = psi_ax;
+        o[7] = psi_b;
+        o[8] = t_izax;
+        o[9] = t_irax;
+        o[10] = t_izx;
+        o[11] = t_irx;
+        o[12] = diff_last;
+        o[13] = t_found;
+        o[14] = scale;
+        o[15] = 0.0;
+      }
+    }
+    __syncthreads();
+  }
+}
+
 }  // namespace gsb
 
 using namespace gsb;
@@ -680,13 +1113,92 @@ static ProfileDev to_dev(const gsb_profile &q) {
   return d;
 }
 
+// Persistent resident solve (k_picard_resident).  Returns GSB_ESTATE (without setting an error) when
+// one equilibrium's V-cycle hierarchy does not fit the shared memory of an SM.
+static int picard_resident_launch(gsb_ctx *ctx, const gsb_picard_params *p, double *psi_dev, const double *bc_dev,
+                                  const double *ip_dev, const double *prof_dev, double *jphi_dev,
+                                  double *summary_dev, double *hist_dev, double *gs_hist_dev, int batch,
+                                  cudaStream_t st) {
+  constexpr int kScratch = 96;
+  RPlan plan;
+  if (!build_rplan(ctx, 0, kScratch, &plan) || plan.nlev < 2) return GSB_ESTATE;
+  const int nz = ctx->nz, nr = ctx->nr, hw = (nr + 1) / 2;
+  // the Jacobi seed borrows the (then idle) planes of the first coarse level as its spare half plane
+  const RLevel &c1 = plan.lev[1];
+  if (4 * c1.nz * c1.hw < nz * hw) return GSB_ESTATE;
+  gsb_picard_ws *w = ctx->picard;
+  const size_t n = ctx->n, planes = (size_t)2 * nz * hw, per_cta = 4 * n + planes;
+  const int grid = std::min(batch, ctx->num_sms);
+  if (w->res_grid < grid) {
+    if (w->res_ws) cudaFree(w->res_ws);
+    w->res_ws = nullptr;
+    w->res_grid = 0;
+    GSB_CUDA(cudaMalloc(&w->res_ws, (size_t)ctx->num_sms * per_cta * sizeof(double)));
+    w->res_grid = ctx->num_sms;
+  }
+  PicardResArgs a{};
+  a.psi = psi_dev;
+  a.bc = bc_dev;
+  a.ip = ip_dev;
+  a.prof_dev = prof_dev;
+  a.jphi = jphi_dev;
+  a.summary = summary_dev;
+  a.hist = hist_dev;
+  a.gs_hist = gs_hist_dev;
+  a.ws_psi = w->res_ws;
+  a.ws_j = w->res_ws + (size_t)w->res_grid * 3 * n;
+  a.ws_src = a.ws_j + (size_t)w->res_grid * n;
+  a.seedJ = w->seedJ;
+  a.cf = w->cf;
+  a.mr = w->mr;
+  a.rrow = ctx->r_dev;
+  a.rowmask = w->rowmask;
+  {
+    volatile double ssum = w->seed_sum * ctx->dr;
+    volatile double ssum2 = ssum * ctx->dz;
+    a.seed_sum_drdz = ssum2;
+  }
+  a.batch = batch;
+  a.max_iter = p->max_iterations;
+  a.seed = p->seed;
+  a.saddle = p->saddle;
+  a.need_gs = p->require_gs_residual;
+  a.tol = p->tol;
+  a.gs_tol = p->gs_tol;
+  a.alpha = p->alpha;
+  a.oma = 1.0 - p->alpha;
+  a.omega = p->omega;
+  a.dr = ctx->dr;
+  a.dz = ctx->dz;
+  {
+    volatile double dr2 = ctx->dr * ctx->dr, dz2 = ctx->dz * ctx->dz, f1 = 4.0 * ctx->dr, f2 = f1 * ctx->dz;
+    a.dr2 = dr2;
+    a.dz2 = dz2;
+    a.four_drdz = f2;
+  }
+  a.gg = make_grad_geom(ctx->dz, ctx->dr);
+  a.prof = to_dev(p->prof);
+  a.scratch_off = plan.pool_doubles + res_stage_doubles(plan.nlev);
+  a.tplane_off = c1.x_off;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GSB_CUDA(cudaFuncSetAttribute(k_picard_resident, cudaFuncAttributeMaxDynamicSharedMemorySize, kResSmemMax));
+    attr_set = true;
+  }
+  const size_t smem = (size_t)(a.scratch_off + kScratch) * sizeof(double);
+  k_picard_resident<<<grid, kResThreads, smem, st>>>(plan, a);
+  GSB_LAUNCH_CHECK();
+  ctx->picard_last_iters = p->max_iterations;  // upper bound: the count lives in summary_dev
+  return GSB_OK;
+}
+
 extern "C" {
 
 void gsb_picard_ws_free(gsb_ctx *ctx) {
   gsb_picard_ws *w = ctx->picard;
   if (!w) return;
   void *ptrs[] = {w->buf1, w->buf2, w->W, w->source, w->ring, w->tpart, w->spart, w->rpart,
-                  w->seedJ, w->cf, w->mr, w->rowmask, w->ints, w->dbls};
+                  w->seedJ, w->cf, w->mr, w->rowmask, w->ints, w->dbls, w->res_ws};
   for (void *q : ptrs)
     if (q) cudaFree(q);
   delete w;
@@ -795,7 +1307,11 @@ int gsb_picard_solve(gsb_ctx *ctx, const gsb_picard_params *p, double *psi_dev, 
   PicardState &s = w->s;
   const int P = partials_for(nz, nr);
   const GradGeom gg = make_grad_geom(ctx->dz, ctx->dr);
-  const int rs = ring_size(nz, nr);
+  if (p->method == 0 && !std::getenv("GSB_PICARD_STREAMING")) {
+    rc = picard_resident_launch(ctx, p, psi_dev, bc_dev, ip_dev, prof_dev, jphi_dev, summary_dev, hist_dev,
+                                gs_hist_dev, batch, st);
+    if (rc != GSB_ESTATE) return rc;  // GSB_ESTATE: one equilibrium does not fit an SM -> streaming path
+  }
   const int copy_blocks = (int)std::min<size_t>((n + 255) / 256, 64);
   const ProfileDev prof = to_dev(p->prof);
 
