@@ -603,6 +603,7 @@ __global__ void k_fill_int(int *p, int v, int n) {
 
 using namespace gsb;
 
+namespace gsb { int picard_phase_read(long long *out64, int reset); }
 static bool omega_ok(double w) { return std::isfinite(w) && w >= 1.0 && w < 2.0; }
 
 extern "C" {
@@ -621,7 +622,7 @@ int gsb_debug_phase_cycles(long long *out64, int reset) {
     for (int i = 0; i < 64; ++i) out64[i] = 0;
   (void)reset;
 #endif
-  return GSB_OK;
+  return picard_phase_read(out64, reset);  // the Picard translation unit has its own counters
 }
 
 int gsb_smooth(gsb_ctx *ctx, double *psi_dev, const double *src_dev, int batch, double omega,

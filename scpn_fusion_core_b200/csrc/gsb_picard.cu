@@ -719,6 +719,7 @@ k_picard_resident(const __grid_constant__ RPlan plan, const __grid_constant__ Pi
     double psi_ax = 0.0, psi_b = 0.0, t_izax = 0, t_irax = 0, t_izx = 0, t_irx = 0, t_found = 0;
 
     for (int k = 0; k < a.max_iter; ++k) {
+      GSB_PHASE_BEGIN();
       // ---- T: topology on the resident planes (a10, a11)
       ValIdx mx{0.0, -1}, mb{0.0, -1};
       double mn = INFINITY;
@@ -826,6 +827,7 @@ k_picard_resident(const __grid_constant__ RPlan plan, const __grid_constant__ Pi
       t_found = res_pool[bslot + 6];
       __syncthreads();
 
+      GSB_PHASE(48);  // topology
       // ---- S1: J_raw(psi) + deterministic block sum (a12)
       double denom = dsub(psi_b, psi_ax);
       if (fabs(denom) < 1e-9) denom = 1e-9;
@@ -862,9 +864,11 @@ k_picard_resident(const __grid_constant__ RPlan plan, const __grid_constant__ Pi
         }
       __syncthreads();
 
+      GSB_PHASE(49);  // source
       // ---- E: one V-cycle on the planes (they hold a copy of the current iterate)
       res_vcycle(lev_off, plan.nlev, wsrc, a.omega, 3, 3);
       __syncthreads();
+      GSB_PHASE(50);  // V-cycle
 
       // ---- R: wall BC, NaN flag, mean|dpsi|, under-relaxation (in place), GS residual
       const double *old = wpsi + (size_t)cur * n;
@@ -885,6 +889,7 @@ k_picard_resident(const __grid_constant__ RPlan plan, const __grid_constant__ Pi
           out[o] = c;
         }
       const int anybad = __syncthreads_or(bad);
+      GSB_PHASE(51);  // relax + diff
       double rmax = 0.0, rsq = 0.0;
       for (int iz = 1 + warp; iz < nz - 1; iz += nw)
         for (int ir = 1 + lane; ir < nr - 1; ir += 32) {
@@ -941,6 +946,8 @@ k_picard_resident(const __grid_constant__ RPlan plan, const __grid_constant__ Pi
       const bool improved = res_pool[bslot + 5] != 0.0;
       __syncthreads();
       iters = k + 1;
+      GSB_PHASE(52);  // GS residual + decide
+      if (blockIdx.x == 0 && threadIdx.x == 0) GSB_PHASE_COUNT(53);
       if (code == 3) {  // revert to the best state (newton_solver.py:518-532)
         status = 3;
         cur = best;
@@ -1115,6 +1122,25 @@ static ProfileDev to_dev(const gsb_profile &q) {
 
 // Persistent resident solve (k_picard_resident).  Returns GSB_ESTATE (without setting an error) when
 // one equilibrium's V-cycle hierarchy does not fit the shared memory of an SM.
+namespace gsb {
+int picard_phase_read(long long *out64, int reset) {
+#ifdef GSB_PHASE_TIMING
+  long long tmp[64];
+  GSB_CUDA(cudaMemcpyFromSymbol(tmp, g_phase, sizeof(tmp)));
+  if (out64)
+    for (int i = 0; i < 64; ++i) out64[i] += tmp[i];
+  if (reset) {
+    long long z[64] = {0};
+    GSB_CUDA(cudaMemcpyToSymbol(g_phase, z, sizeof(z)));
+  }
+#else
+  (void)out64;
+  (void)reset;
+#endif
+  return GSB_OK;
+}
+}  // namespace gsb
+
 static int picard_resident_launch(gsb_ctx *ctx, const gsb_picard_params *p, double *psi_dev, const double *bc_dev,
                                   const double *ip_dev, const double *prof_dev, double *jphi_dev,
                                   double *summary_dev, double *hist_dev, double *gs_hist_dev, int batch,

@@ -65,9 +65,11 @@ __device__ long long g_phase[64];
       _pt = _now;                                           \
     }                                                       \
   } while (0)
+#define GSB_PHASE_COUNT(idx) g_phase[(idx)] += 1
 #else
 #define GSB_PHASE_BEGIN() do {} while (0)
 #define GSB_PHASE(idx) do {} while (0)
+#define GSB_PHASE_COUNT(idx) do {} while (0)
 #endif
 
 __device__ __forceinline__ int split_index(int nz, int hw, int iz, int ir) {

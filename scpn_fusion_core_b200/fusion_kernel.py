@@ -586,7 +586,7 @@ class BatchedFusionKernel(_GridMixin):
         }
 
     def solve_device(self, w_dev, ip_dev, ped_dev=None, *, want_history: bool = False, psi_out=None,
-                     jphi_out=None) -> dict[str, Any]:
+                     jphi_out=None, events=None) -> dict[str, Any]:
         """Device-resident batch solve: no host<->device traffic except the active-count poll.
 
         w_dev (B, n_coils) = (mu0*I)/(2 pi) per coil, ip_dev (B,), ped_dev (B, 8) or None; all CUDA
@@ -609,10 +609,14 @@ class BatchedFusionKernel(_GridMixin):
             hist = D.zeros((B, params.max_iterations), self.device)
             gsh = D.zeros((B, params.max_iterations), self.device)
         null = ctypes.c_void_p()
+        if events is not None:  # (start, stop) CUDA events bracketing the Picard launch (bench.py roofline)
+            events[0].record()
         _lib.check(ctx.lib.gsb_picard_solve(ctx.handle, ctypes.byref(params), D.ptr(psi), D.ptr(bc), D.ptr(ip_dev),
                                             null if ped_dev is None else D.ptr(ped_dev), D.ptr(jphi), D.ptr(summ),
                                             null if hist is None else D.ptr(hist), null if gsh is None else D.ptr(gsh),
                                             B, st), "gsb_picard_solve")
+        if events is not None:
+            events[1].record()
         out = {"psi": psi, "j_phi": jphi, "summary": summ}
         if want_history:
             out["hist"], out["gs_hist"] = hist, gsh
