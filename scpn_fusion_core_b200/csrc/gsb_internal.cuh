@@ -244,7 +244,7 @@ __device__ __forceinline__ double hypot_kernel(double ax, double ay) {
   }
   return dsub(h, __ddiv_rn(dadd(t1, t2), dmul(2.0, h)));
 }
-__device__ __forceinline__ double hypot_glibc(double x, double y) {
+static __device__ __noinline__ double hypot_glibc_slow(double x, double y) {
   if (isinf(x) || isinf(y)) return INFINITY;
   if (isnan(x) || isnan(y)) return dadd(x, y);
   x = fabs(x);
@@ -261,6 +261,17 @@ __device__ __forceinline__ double hypot_glibc(double x, double y) {
   }
   if (ax >= dmul(ay, 0x1p+54)) return dadd(ax, ay);
   return hypot_kernel(ax, ay);
+}
+__device__ __forceinline__ double hypot_glibc(double x, double y) {
+  const double fx = fabs(x), fy = fabs(y);
+  const double ax = fx < fy ? fy : fx;
+  const double ay = fx < fy ? fx : fy;
+  // common case (no scaling, no shortcut, nothing non-finite: NaN fails every comparison)
+  if (ax <= 0x1p+511 && ay >= 0x1p-459 && ax < dmul(ay, 0x1p+54)) return hypot_kernel(ax, ay);
+  return hypot_glibc_slow(x, y);
+}
+__device__ __forceinline__ double sanitize_fast(double v) {
+  return (fabs(v) <= kCap) ? v : sanitize(v);  // identity for in-range finite values (the common case)
 }
 
 }  // namespace gsb

@@ -401,6 +401,7 @@ bool build_rplan(const gsb_ctx *ctx, int l0, int extra_doubles, RPlan *out) {
       r.rpc += 1;
       r.nch = (rows + r.rpc - 1) / r.rpc;
     }
+    if (l == l0 && r.rpc > kResMaxRun) return false;  // the finest level prefetches a whole run's rhs into registers
     const int ncj = std::max(r.nr - 2, 1);
     r.lj = 0;
     while ((1 << r.lj) < ncj) ++r.lj;

@@ -42,7 +42,7 @@ struct gsb_picard_ws {
   // cached host-side parameters the device tables were built for
   double mu0 = NAN, z_min = NAN, r_min = NAN, r_max = NAN;
   double seed_sum = 0.0;
-  // private per-CTA workspace of the persistent resident solve: [grid][4*n + 2*nz*hw]
+  // private per-CTA workspace of the persistent resident solve: [grid][5 * 2*nz*hw] (colour-split)
   double *res_ws = nullptr;
   int res_grid = 0;
 };
@@ -568,8 +568,13 @@ k_bfield(const double *__restrict__ psi, int nz, int nr, GradGeom gg, const doub
 // equilibrium (seed, every Picard iteration, V-cycles, convergence logic) and then fetches the
 // next one.  psi lives in the colour-split shared-memory planes (gsb_resident.cuh) for the whole
 // solve; the only per-iteration global traffic is the CTA's private, L2-resident workspace
-// (previous iterate, J, split right-hand side).  No host polling, no launch per phase, and an
-// equilibrium stops the moment it converges instead of waiting for the slowest of the batch.
+// (previous iterate, J, right-hand side - all in the same colour-split layout).  No host polling,
+// no launch per phase, and an equilibrium stops the moment it converges instead of waiting for the
+// slowest of the batch.
+//
+// Element-wise phases walk the "slots" e = iz*hw + k (column pair 2k, 2k+1 of row iz) with stride
+// blockDim.x: x(iz,2k) = plane[iz&1][e], x(iz,2k+1) = plane[(iz+1)&1][e], so both planes are read
+// and written unit-stride and (iz, k) are tracked incrementally (no integer division in loops).
 // ============================================================================================
 struct PicardResArgs {
   double *psi;              // [B][n] in: initial flux, out: solution
@@ -579,9 +584,9 @@ struct PicardResArgs {
   double *jphi;             // [B][n] out
   double *summary;          // [B][16] out
   double *hist, *gs_hist;   // NULL or [B][max_iter]
-  double *ws_psi;           // [grid][3][n]   iterate rotation (cur / next / best)
-  double *ws_j;             // [grid][n]      J_raw -> J_phi
-  double *ws_src;           // [grid][2*nz*hw] right-hand side, colour-split
+  double *ws_psi;           // [grid][3][2*nz*hw]  iterate rotation (cur / next / best), colour-split
+  double *ws_j;             // [grid][2*nz*hw]     J_raw -> J_phi, colour-split
+  double *ws_src;           // [grid][2*nz*hw]     right-hand side, colour-split
   const double *seedJ, *cf, *mr, *rrow;
   const int *rowmask;
   double seed_sum_drdz;
@@ -598,7 +603,8 @@ __device__ __forceinline__ double pl(int xo, int nz, int hw, int iz, int ir) {
   return res_pool[xo + split_index(nz, hw, iz, ir)];
 }
 
-// np.gradient on the resident planes (same arithmetic as grad_point)
+// np.gradient on the resident planes (same arithmetic as grad_point); generic accessor, used by the
+// saddle filter only
 __device__ __forceinline__ void grad_planes(int xo, int nz, int nr, int hw, int iz, int ir, const GradGeom &gg,
                                             double &gz, double &gr) {
   const double c = pl(xo, nz, hw, iz, ir);
@@ -616,6 +622,85 @@ __device__ __forceinline__ void grad_planes(int xo, int nz, int nr, int hw, int 
     gr = ddiv_y(dsub(pl(xo, nz, hw, iz, ir + 1), pl(xo, nz, hw, iz, ir - 1)), gg.two_dr, gg.inv_two_dr);
 }
 
+// |grad psi| of one point from its own value and its four neighbours (np.gradient semantics:
+// centred differences inside, one-sided first-order differences on the edges), np.hypot
+__device__ __forceinline__ double grad_mag(const GradGeom &gg, double c, double up, double down, double left,
+                                           double right, bool z_lo, bool z_hi, bool r_lo, bool r_hi) {
+  double gz, gr;
+  if (z_lo)
+    gz = ddiv_yf(dsub(up, c), gg.dz, gg.inv_dz);
+  else if (z_hi)
+    gz = ddiv_yf(dsub(c, down), gg.dz, gg.inv_dz);
+  else
+    gz = ddiv_yf(dsub(up, down), gg.two_dz, gg.inv_two_dz);
+  if (r_lo)
+    gr = ddiv_yf(dsub(right, c), gg.dr, gg.inv_dr);
+  else if (r_hi)
+    gr = ddiv_yf(dsub(c, left), gg.dr, gg.inv_dr);
+  else
+    gr = ddiv_yf(dsub(right, left), gg.two_dr, gg.inv_two_dr);
+  return hypot_glibc(gr, gz);
+}
+
+// mtanh profile (fusion_kernel.py:380-389) with the two per-equilibrium divisors pre-inverted
+// (correctly rounded Markstein division == the IEEE quotient)
+struct MtanhK {
+  double top, width, half_h, alpha, inv_top, inv_width;
+};
+__device__ __forceinline__ MtanhK mtanh_k(const double *q) {
+  MtanhK m;
+  m.top = q[0], m.width = q[1], m.half_h = dmul(0.5, q[2]), m.alpha = q[3];
+  m.inv_top = __ddiv_rn(1.0, q[0]);
+  m.inv_width = __ddiv_rn(1.0, q[1]);
+  return m;
+}
+// tanh(y) for |y| <= 20 as (1 - u)/(1 + u), u = exp(-2y): Cody-Waite reduction, degree-13 Taylor
+// polynomial on |r| <= ln2/2 (truncation 4e-18 relative), exponent add, then a Newton-refined
+// reciprocal.  Absolute error <= 3e-16 over the range (np.tanh itself is only accurate to ~1 ulp of
+// a result that is then added to 1.0), ~30 instructions instead of ~90 for the library tanh().
+__device__ __forceinline__ double tanh_lean(double y) {
+  const double x = -2.0 * y;  // exact
+  const int k = __double2int_rn(x * 1.4426950408889634074);
+  const double kf = (double)k;
+  double r = __fma_rn(-kf, 6.93147180369123816490e-01, x);
+  r = __fma_rn(-kf, 1.90821492927058770002e-10, r);
+  double p = 1.6059043836821613e-10;  // 1/13!
+  p = __fma_rn(p, r, 2.08767569878681e-09);
+  p = __fma_rn(p, r, 2.505210838544172e-08);
+  p = __fma_rn(p, r, 2.755731922398589e-07);
+  p = __fma_rn(p, r, 2.7557319223985893e-06);
+  p = __fma_rn(p, r, 2.48015873015873e-05);
+  p = __fma_rn(p, r, 1.984126984126984e-04);
+  p = __fma_rn(p, r, 1.388888888888889e-03);
+  p = __fma_rn(p, r, 8.333333333333333e-03);
+  p = __fma_rn(p, r, 4.1666666666666664e-02);
+  p = __fma_rn(p, r, 1.6666666666666666e-01);
+  p = __fma_rn(p, r, 0.5);
+  p = __fma_rn(p, r, 1.0);
+  p = __fma_rn(p, r, 1.0);
+  const double u = __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));  // |k| <= 58: no over/underflow
+  const double d = 1.0 + u, n = 1.0 - u;
+  double y0;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(d));
+  double e = __fma_rn(-d, y0, 1.0);
+  y0 = __fma_rn(y0, e, y0);
+  e = __fma_rn(-d, y0, 1.0);
+  y0 = __fma_rn(y0, e, y0);
+  const double q = n * y0;
+  return __fma_rn(__fma_rn(-d, q, n), y0, q);
+}
+__device__ __forceinline__ double mtanh_res(double x, const MtanhK &m) {
+  double y = ddiv_yf(dsub(m.top, x), m.width, m.inv_width);
+  y = fmin(fmax(y, -20.0), 20.0);
+  const double ped = dmul(m.half_h, dadd(1.0, tanh_lean(y)));
+  double core = 0.0;
+  if (x < m.top) {
+    const double t = ddiv_yf(x, m.top, m.inv_top);
+    core = fmax(0.0, dsub(1.0, dmul(t, t)));
+  }
+  return dadd(ped, dmul(m.alpha, core));
+}
+
 // block-wide broadcast of a value computed by thread 0 (through the scratch area)
 __device__ __forceinline__ double bcast_d(double v, int slot_off) {
   __syncthreads();
@@ -627,17 +712,45 @@ __device__ __forceinline__ double bcast_d(double v, int slot_off) {
 __global__ void __launch_bounds__(kResThreads, 1)
 k_picard_resident(const __grid_constant__ RPlan plan, const __grid_constant__ PicardResArgs a) {
   const int lev_off = res_stage(plan);
-  const RLevel &F = res_level(lev_off, 0);
-  const int nz = F.nz, nr = F.nr, hw = F.hw, xo = F.x_off;
-  const int n = nz * nr, planes = 2 * nz * hw;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  int nz, nr, hw, xo, f_lk, f_nch, f_rpc, f_nk;
+  ResK rk;
+  {
+    const RLevel &F = res_level(lev_off, 0);
+    nz = F.nz, nr = F.nr, hw = F.hw, xo = F.x_off, f_lk = F.lk, f_nch = F.nch, f_rpc = F.rpc, f_nk = F.nk;
+    rk = res_load_resk(F.g);
+  }
+  const double *tab_ae = plan.lev[0].g.a_e;  // a_e | a_w (global)
+  const double *tab_rs = plan.lev[0].g.r_safe, *tab_irs = plan.lev[0].g.inv_r_safe;
+  const double a_ns0 = plan.lev[0].g.a_ns, a_c0 = plan.lev[0].g.a_c, inv_a_c0 = plan.lev[0].g.inv_a_c;
+  const int n = nz * nr, ps = nz * hw, planes = 2 * ps, nslot = ps;
+  const int tid = threadIdx.x, T = blockDim.x;
+  const int lane = tid & 31, warp = tid >> 5, nw = T >> 5;
+  const int step_z = T / hw, step_k = T - step_z * hw;
+  const int iz_first = tid / hw, k_first = tid - iz_first * hw;
   double *sh = res_pool + a.scratch_off;            // 32 doubles reduction scratch
   int *shi = reinterpret_cast<int *>(sh + 32);       // 32 ints (16 doubles)
   const int bslot = a.scratch_off + 48;              // broadcast slots
-  double *wpsi = a.ws_psi + (size_t)blockIdx.x * 3 * n;
-  double *wj = a.ws_j + (size_t)blockIdx.x * n;
+  double *wpsi = a.ws_psi + (size_t)blockIdx.x * 3 * planes;
+  double *wj = a.ws_j + (size_t)blockIdx.x * planes;
   double *wsrc = a.ws_src + (size_t)blockIdx.x * planes;
   const double n_all = (double)n, n_int = (double)(nz - 2) * (double)(nr - 2);
+  const bool odd_nr = (nr & 1) != 0;  // then slot k = hw-1 holds only the (even) wall column
+
+// slot loop: e = tid, tid+T, ... ; (iz, k) tracked incrementally; pa/pb = plane offsets (without the
+// pool base) of the even / odd column of the slot; has_odd = the odd column exists
+#define GSB_SLOT_LOOP_BEGIN()                                                  \
+  for (int e = tid, iz = iz_first, k = k_first; e < nslot; e += T) {          \
+    const int par_ = iz & 1;                                                   \
+    const int pa = par_ * ps + e, pb = (1 - par_) * ps + e;                    \
+    const bool has_odd = odd_nr ? (k < hw - 1) : true;
+#define GSB_SLOT_LOOP_END()                                                    \
+    k += step_k;                                                               \
+    iz += step_z;                                                              \
+    if (k >= hw) {                                                             \
+      k -= hw;                                                                 \
+      ++iz;                                                                    \
+    }                                                                          \
+  }
 
   for (int b = blockIdx.x; b < a.batch; b += gridDim.x) {
     const double *bc = a.bc + (size_t)b * n;
@@ -648,16 +761,18 @@ k_picard_resident(const __grid_constant__ RPlan plan, const __grid_constant__ Pi
       pp[i] = a.prof_dev ? a.prof_dev[(size_t)b * 8 + i] : a.prof.p[i];
       pf[i] = a.prof_dev ? a.prof_dev[(size_t)b * 8 + 4 + i] : a.prof.f[i];
     }
+    const MtanhK mkp = mtanh_k(pp), mkf = mtanh_k(pf);
+    const bool same_prof = pp[0] == pf[0] && pp[1] == pf[1] && pp[2] == pf[2] && pp[3] == pf[3];
     // ---- initial flux -> planes; pre-seed copy is the initial "best" state (newton_solver.py:484)
     __syncthreads();
     res_load_dense(a.psi + (size_t)b * n, xo, nz, nr, hw);
     int cur = 0, best = 0, nxt = 1;
     const bool do_seed = a.seed && fabs(ipb) >= 1e-12;
+    __syncthreads();
     if (a.seed) {
-      for (int i = threadIdx.x; i < n; i += blockDim.x) wpsi[2 * n + i] = a.psi[(size_t)b * n + i];
+      for (int i = tid; i < planes; i += T) wpsi[2 * planes + i] = res_pool[xo + i];
       best = 2;
     }
-    __syncthreads();
 
     // ---- seed: Gaussian source scaled to Ip, 50 sanitised/clipped Jacobi steps (iterative_solver.py:384-410)
     if (do_seed) {
@@ -665,12 +780,12 @@ k_picard_resident(const __grid_constant__ RPlan plan, const __grid_constant__ Pi
       for (int iz = warp; iz < nz; iz += nw)
         for (int ir = lane; ir < nr; ir += 32) {
           const double j = dmul(a.seedJ[iz * nr + ir], sc);
-          wj[iz * nr + ir] = j;
-          wsrc[split_index(nz, hw, iz, ir)] = dmul(a.mr[ir], j);
+          const int o = split_index(nz, hw, iz, ir);
+          wj[o] = j;
+          wsrc[o] = dmul(a.mr[ir], j);
         }
       __syncthreads();
-      int p0 = xo, p1 = xo + nz * hw, pt = a.tplane_off;  // colour-0 plane, colour-1 plane, spare
-      const double *tab = F.g.a_e;
+      int p0 = xo, p1 = xo + ps, pt = a.tplane_off;  // colour-0 plane, colour-1 plane, spare
       for (int step = 0; step < 50; ++step) {
 #pragma unroll 1
         for (int c = 0; c < 2; ++c) {
@@ -687,17 +802,17 @@ k_picard_resident(const __grid_constant__ RPlan plan, const __grid_constant__ Pi
               const int o = iz * hw + k;
               double v;
               if (iz == 0 || iz == nz - 1 || ir == 0 || ir == nr - 1) {
-                v = sanitize(res_pool[src_plane + o]);
+                v = sanitize_fast(res_pool[src_plane + o]);
               } else {
-                const double cc = sanitize(res_pool[oth_plane + o]);
-                const double side = sanitize(res_pool[oth_plane + o - 1 + 2 * s]);
-                const double S = sanitize(res_pool[oth_plane + o - hw]), N = sanitize(res_pool[oth_plane + o + hw]);
-                const double f = sanitize(wsrc[c * nz * hw + o]);
-                double acc = dadd(dmul(tab[ir], s ? side : cc), dmul(tab[nr + ir], s ? cc : side));
-                acc = dadd(acc, dmul(F.g.a_ns, S));
-                acc = dadd(acc, dmul(F.g.a_ns, N));
+                const double cc = sanitize_fast(res_pool[oth_plane + o]);
+                const double side = sanitize_fast(res_pool[oth_plane + o - 1 + 2 * s]);
+                const double S = sanitize_fast(res_pool[oth_plane + o - hw]), N = sanitize_fast(res_pool[oth_plane + o + hw]);
+                const double f = sanitize_fast(__ldcg(wsrc + c * ps + o));
+                double acc = dadd(dmul(__ldg(tab_ae + ir), s ? side : cc), dmul(__ldg(tab_ae + nr + ir), s ? cc : side));
+                acc = dadd(acc, dmul(a_ns0, S));
+                acc = dadd(acc, dmul(a_ns0, N));
                 acc = dsub(acc, f);
-                v = clip_cap(ddiv_y(acc, F.g.a_c, F.g.inv_a_c));
+                v = clip_cap(ddiv_y(acc, a_c0, inv_a_c0));
               }
               res_pool[dst_plane + o] = v;
             }
@@ -711,33 +826,48 @@ k_picard_resident(const __grid_constant__ RPlan plan, const __grid_constant__ Pi
       // 50 swaps: colour 0 is back in its home plane
     }
     // current iterate -> workspace slot `cur`
-    res_store_dense(wpsi + (size_t)cur * n, xo, nz, nr, hw);
+    __syncthreads();
+    for (int i = tid; i < planes; i += T) wpsi[(size_t)cur * planes + i] = res_pool[xo + i];
     __syncthreads();
 
     int status = 0, iters = 0;
     double diff_best = 1e9, gs_best = INFINITY, gs_last = INFINITY, diff_last = 0.0, scale = 0.0;
     double psi_ax = 0.0, psi_b = 0.0, t_izax = 0, t_irax = 0, t_izx = 0, t_irx = 0, t_found = 0;
 
-    for (int k = 0; k < a.max_iter; ++k) {
+    for (int kit = 0; kit < a.max_iter; ++kit) {
       GSB_PHASE_BEGIN();
       // ---- T: topology on the resident planes (a10, a11)
       ValIdx mx{0.0, -1}, mb{0.0, -1};
       double mn = INFINITY;
-      for (int iz = warp; iz < nz; iz += nw) {
-        const bool div = a.rowmask[iz] != 0;
-        for (int ir = lane; ir < nr; ir += 32) {
-          const int flat = iz * nr + ir;
-          const double v = pl(xo, nz, hw, iz, ir);
-          mx = better<true>(mx, ValIdx{v, flat});
-          mn = fmin(mn, v);
-          if (div) {
-            double gz, gr;
-            grad_planes(xo, nz, nr, hw, iz, ir, a.gg, gz, gr);
-            const double bm = hypot_glibc(gr, gz);
+      GSB_SLOT_LOOP_BEGIN()
+        const int flat = iz * nr + 2 * k;
+        const double ve = res_pool[xo + pa];
+        const double vo = has_odd ? res_pool[xo + pb] : ve;
+        // a thread visits flat indices in increasing order, so a strict > keeps the first maximum
+        if (ve > mx.v || mx.i < 0) mx = ValIdx{ve, flat};
+        mn = fmin(mn, ve);
+        if (has_odd) {
+          if (vo > mx.v) mx = ValIdx{vo, flat + 1};
+          mn = fmin(mn, vo);
+        }
+        if (__ldg(a.rowmask + iz) != 0) {
+          const bool z_lo = iz == 0, z_hi = iz == nz - 1;
+          // even column 2k: vertical neighbours and the odd columns either side live in plane pb
+          {
+            const double up = z_hi ? 0.0 : res_pool[xo + pb + hw], down = z_lo ? 0.0 : res_pool[xo + pb - hw];
+            const double left = k > 0 ? res_pool[xo + pb - 1] : 0.0;
+            const double bm = grad_mag(a.gg, ve, up, down, left, vo, z_lo, z_hi, k == 0, !has_odd);
             if (isfinite(bm)) mb = better<false>(mb, ValIdx{bm, flat});
           }
+          if (has_odd) {  // odd column 2k+1: neighbours in plane pa
+            const bool r_hi = 2 * k + 1 == nr - 1;
+            const double up = z_hi ? 0.0 : res_pool[xo + pa + hw], down = z_lo ? 0.0 : res_pool[xo + pa - hw];
+            const double right = r_hi ? 0.0 : res_pool[xo + pa + 1];
+            const double bm = grad_mag(a.gg, vo, up, down, ve, right, z_lo, z_hi, false, r_hi);
+            if (isfinite(bm)) mb = better<false>(mb, ValIdx{bm, flat + 1});
+          }
         }
-      }
+      GSB_SLOT_LOOP_END()
       mx = block_arg<true>(mx, sh, shi);
       __syncthreads();
       mb = block_arg<false>(mb, sh, shi);
@@ -826,81 +956,182 @@ k_picard_resident(const __grid_constant__ RPlan plan, const __grid_constant__ Pi
       t_irx = res_pool[bslot + 5];
       t_found = res_pool[bslot + 6];
       __syncthreads();
-
       GSB_PHASE(48);  // topology
+
       // ---- S1: J_raw(psi) + deterministic block sum (a12)
       double denom = dsub(psi_b, psi_ax);
       if (fabs(denom) < 1e-9) denom = 1e-9;
       const double inv_denom = __ddiv_rn(1.0, denom);
+      const bool hmode = a.prof.hmode != 0;
       double acc = 0.0;
-      for (int iz = warp; iz < nz; iz += nw)
-        for (int ir = lane; ir < nr; ir += 32) {
-          const double pn = ddiv_y(dsub(pl(xo, nz, hw, iz, ir), psi_ax), denom, inv_denom);
-          double pr = 0.0, ff = 0.0;
-          if (pn >= 0.0 && pn < 1.0) {
-            if (a.prof.hmode) {
-              pr = mtanh_dev(pn, pp);
-              ff = mtanh_dev(pn, pf);
-            } else {
-              pr = dsub(1.0, pn);
-              ff = pr;
+      GSB_SLOT_LOOP_BEGIN()
+        const double pn_e = ddiv_yf(dsub(res_pool[xo + pa], psi_ax), denom, inv_denom);
+        const double pn_o = has_odd ? ddiv_yf(dsub(res_pool[xo + pb], psi_ax), denom, inv_denom) : -1.0;
+        const bool in_e = pn_e >= 0.0 && pn_e < 1.0, in_o = pn_o >= 0.0 && pn_o < 1.0;
+        double pr_e = 0.0, ff_e = 0.0, pr_o = 0.0, ff_o = 0.0;
+        if (in_e || in_o) {
+          // both points in straight-line code (two independent chains); out-of-plasma results are discarded
+          if (hmode) {
+            const double te = mtanh_res(pn_e, mkp), to = mtanh_res(pn_o, mkp);
+            double fe = te, fo = to;
+            if (!same_prof) {
+              fe = mtanh_res(pn_e, mkf);
+              fo = mtanh_res(pn_o, mkf);
             }
+            pr_e = in_e ? te : 0.0, ff_e = in_e ? fe : 0.0;
+            pr_o = in_o ? to : 0.0, ff_o = in_o ? fo : 0.0;
+          } else {
+            pr_e = ff_e = in_e ? dsub(1.0, pn_e) : 0.0;
+            pr_o = ff_o = in_o ? dsub(1.0, pn_o) : 0.0;
           }
-          const double j = dadd(dmul(0.5, dmul(a.rrow[ir], pr)), dmul(0.5, dmul(a.cf[ir], ff)));
-          wj[iz * nr + ir] = j;
-          acc += j;
         }
+        // J_raw = 0.5*(R*p) + 0.5*((1/(mu0 R))*ff)      (fusion_kernel.py:430-434)
+        const double je = dadd(dmul(0.5, dmul(__ldg(a.rrow + 2 * k), pr_e)), dmul(0.5, dmul(__ldg(a.cf + 2 * k), ff_e)));
+        __stcg(wj + pa, je);
+        acc += je;
+        if (has_odd) {
+          const double jo = dadd(dmul(0.5, dmul(__ldg(a.rrow + 2 * k + 1), pr_o)), dmul(0.5, dmul(__ldg(a.cf + 2 * k + 1), ff_o)));
+          __stcg(wj + pb, jo);
+          acc += jo;
+        }
+      GSB_SLOT_LOOP_END()
       acc = block_sum(acc, sh);
       const double jsum = bcast_d(acc, bslot + 8);
       // ---- S2: J = J_raw * Ip/I ; Source = (-mu0 R) J   (split layout)
       const double icur = dmul(dmul(jsum, a.dr), a.dz);
       const bool ok = fabs(icur) > 1e-9;
       scale = ok ? __ddiv_rn(ipb, icur) : 0.0;
-      for (int iz = warp; iz < nz; iz += nw)
-        for (int ir = lane; ir < nr; ir += 32) {
-          const double j = ok ? dmul(wj[iz * nr + ir], scale) : 0.0;
-          wj[iz * nr + ir] = j;
-          wsrc[split_index(nz, hw, iz, ir)] = dmul(a.mr[ir], j);
+      {  // batches of four slots: all loads of a batch are in flight before the first use
+        int e = tid, iz = iz_first, k = k_first;
+        while (e < nslot) {
+          double vje[4], vjo[4];
+          int vpa[4], vpb[4], vk[4];
+          bool vok[4], vho[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int par_ = iz & 1;
+            vok[u] = e < nslot;
+            vpa[u] = par_ * ps + e, vpb[u] = (1 - par_) * ps + e, vk[u] = k;
+            vho[u] = odd_nr ? (k < hw - 1) : true;
+            vje[u] = vok[u] ? __ldcg(wj + vpa[u]) : 0.0;
+            vjo[u] = (vok[u] && vho[u]) ? __ldcg(wj + vpb[u]) : 0.0;
+            e += T, k += step_k, iz += step_z;
+            if (k >= hw) k -= hw, ++iz;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (vok[u]) {
+              const double je = ok ? dmul(vje[u], scale) : 0.0;
+              __stcg(wj + vpa[u], je);
+              __stcg(wsrc + vpa[u], dmul(__ldg(a.mr + 2 * vk[u]), je));
+              if (vho[u]) {
+                const double jo = ok ? dmul(vjo[u], scale) : 0.0;
+                __stcg(wj + vpb[u], jo);
+                __stcg(wsrc + vpb[u], dmul(__ldg(a.mr + 2 * vk[u] + 1), jo));
+              }
+            }
+          }
         }
+      }
       __syncthreads();
-
       GSB_PHASE(49);  // source
+
       // ---- E: one V-cycle on the planes (they hold a copy of the current iterate)
       res_vcycle(lev_off, plan.nlev, wsrc, a.omega, 3, 3);
       __syncthreads();
       GSB_PHASE(50);  // V-cycle
 
-      // ---- R: wall BC, NaN flag, mean|dpsi|, under-relaxation (in place), GS residual
-      const double *old = wpsi + (size_t)cur * n;
-      double *out = wpsi + (size_t)nxt * n;
+      // ---- R: wall BC, NaN flag, mean|dpsi|, under-relaxation (in place)
+      const double *old = wpsi + (size_t)cur * planes;
+      double *out = wpsi + (size_t)nxt * planes;
       double dsum = 0.0;
       int bad = 0;
-      for (int iz = warp; iz < nz; iz += nw)
-        for (int ir = lane; ir < nr; ir += 32) {
-          const int o = iz * nr + ir;
-          const int so = xo + split_index(nz, hw, iz, ir);
-          const bool wall = iz == 0 || iz == nz - 1 || ir == 0 || ir == nr - 1;
-          const double wn = wall ? bc[o] : res_pool[so];
-          const double ov = old[o];
-          if (isnan(wn) || isinf(wn)) bad = 1;
-          dsum += fabs(dsub(wn, ov));
-          const double c = dadd(dmul(a.oma, ov), dmul(a.alpha, wn));
-          res_pool[so] = c;
-          out[o] = c;
+      {  // batches of four slots (see S2)
+        int e = tid, iz = iz_first, k = k_first;
+        while (e < nslot) {
+          double voe[4], voo[4];
+          int vpa[4], vpb[4], vk[4], vz[4];
+          bool vok[4], vho[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int par_ = iz & 1;
+            vok[u] = e < nslot;
+            vpa[u] = par_ * ps + e, vpb[u] = (1 - par_) * ps + e, vk[u] = k, vz[u] = iz;
+            vho[u] = odd_nr ? (k < hw - 1) : true;
+            voe[u] = vok[u] ? __ldcg(old + vpa[u]) : 0.0;
+            voo[u] = (vok[u] && vho[u]) ? __ldcg(old + vpb[u]) : 0.0;
+            e += T, k += step_k, iz += step_z;
+            if (k >= hw) k -= hw, ++iz;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (vok[u]) {
+              const bool zwall = vz[u] == 0 || vz[u] == nz - 1;
+              {
+                const bool wall = zwall || vk[u] == 0 || !vho[u];  // column 0, or the lone even wall column nr-1
+                const double wn = wall ? bc[vz[u] * nr + 2 * vk[u]] : res_pool[xo + vpa[u]];
+                const double ov = voe[u];
+                if (!(fabs(wn) <= 1.79769313486231570815e308)) bad = 1;  // NaN or +-inf
+                dsum += fabs(dsub(wn, ov));
+                const double c = dadd(dmul(a.oma, ov), dmul(a.alpha, wn));
+                res_pool[xo + vpa[u]] = c;
+                __stcg(out + vpa[u], c);
+              }
+              if (vho[u]) {
+                const bool wall = zwall || (2 * vk[u] + 1 == nr - 1);
+                const double wn = wall ? bc[vz[u] * nr + 2 * vk[u] + 1] : res_pool[xo + vpb[u]];
+                const double ov = voo[u];
+                if (!(fabs(wn) <= 1.79769313486231570815e308)) bad = 1;
+                dsum += fabs(dsub(wn, ov));
+                const double c = dadd(dmul(a.oma, ov), dmul(a.alpha, wn));
+                res_pool[xo + vpb[u]] = c;
+                __stcg(out + vpb[u], c);
+              }
+            }
+          }
         }
+      }
       const int anybad = __syncthreads_or(bad);
       GSB_PHASE(51);  // relax + diff
+      // ---- G: GS residual of the relaxed iterate (compute_gs_residual_rms): thread <-> (k slot,
+      // row chunk) of level 0, both columns of the slot, register window sliding down the rows
       double rmax = 0.0, rsq = 0.0;
-      for (int iz = 1 + warp; iz < nz - 1; iz += nw)
-        for (int ir = 1 + lane; ir < nr - 1; ir += 32) {
-          const double r = dsub(gs_apply(F.g, ir, pl(xo, nz, hw, iz, ir), pl(xo, nz, hw, iz, ir + 1),
-                                         pl(xo, nz, hw, iz, ir - 1), pl(xo, nz, hw, iz - 1, ir),
-                                         pl(xo, nz, hw, iz + 1, ir)),
-                                wsrc[split_index(nz, hw, iz, ir)]);
-          const double ar = fabs(r);
-          if (ar > rmax) rmax = ar;
-          rsq += r * r;
+      {
+        const int k = tid & ((1 << f_lk) - 1), ch = tid >> f_lk;
+        const int z0 = 1 + ch * f_rpc;
+        const int z1 = min(z0 + f_rpc, nz - 1);
+        if (ch < f_nch && k < f_nk && z0 < z1) {
+          const int ce = 2 * k, co = 2 * k + 1;
+          const bool e_in = ce >= 1 && ce <= nr - 2, o_in = co <= nr - 2;
+          const double rs_e = __ldg(tab_rs + ce), irs_e = __ldg(tab_irs + ce);
+          const double rs_o = o_in ? __ldg(tab_rs + co) : 1.0, irs_o = o_in ? __ldg(tab_irs + co) : 1.0;
+          int e = z0 * hw + k;
+          int par = z0 & 1;
+          double ev_m = res_pool[xo + (1 - par) * ps + e - hw], od_m = res_pool[xo + par * ps + e - hw];
+          double ev_0 = res_pool[xo + par * ps + e], od_0 = res_pool[xo + (1 - par) * ps + e];
+          for (int iz = z0; iz < z1; ++iz) {
+            const int pa = par * ps + e, pb = (1 - par) * ps + e;
+            // row iz+1: the even column sits in plane 1-par, the odd column in plane par
+            const double ev_p = res_pool[xo + pb + hw], od_p = res_pool[xo + pa + hw];
+            if (e_in) {
+              const double w = res_pool[xo + pb - 1];
+              const double r = dsub(res_lx(rk, rs_e, irs_e, ev_0, od_0, w, ev_m, ev_p), __ldcg(wsrc + pa));
+              rmax = fmax(rmax, fabs(r));
+              rsq += r * r;
+            }
+            if (o_in) {
+              const double ee = res_pool[xo + pa + 1];
+              const double r = dsub(res_lx(rk, rs_o, irs_o, od_0, ee, ev_0, od_m, od_p), __ldcg(wsrc + pb));
+              rmax = fmax(rmax, fabs(r));
+              rsq += r * r;
+            }
+            ev_m = ev_0, ev_0 = ev_p;
+            od_m = od_0, od_0 = od_p;
+            e += hw;
+            par ^= 1;
+          }
         }
+      }
       dsum = block_sum(dsum, sh);
       __syncthreads();
       rmax = block_max(rmax, sh);
@@ -916,8 +1147,8 @@ k_picard_resident(const __grid_constant__ RPlan plan, const __grid_constant__ Pi
         } else {
           const double diff = dsum / n_all;
           const double gs = (rmax > 0.0 && n_int > 0.0) ? sqrt(rsq / n_int) : 0.0;
-          if (a.hist) a.hist[(size_t)b * a.max_iter + k] = diff;
-          if (a.gs_hist) a.gs_hist[(size_t)b * a.max_iter + k] = gs;
+          if (a.hist) a.hist[(size_t)b * a.max_iter + kit] = diff;
+          if (a.gs_hist) a.gs_hist[(size_t)b * a.max_iter + kit] = gs;
           dl = diff;
           gl = gs;
           if (gs < gbest) gbest = gs;
@@ -927,7 +1158,7 @@ k_picard_resident(const __grid_constant__ RPlan plan, const __grid_constant__ Pi
           }
           if (diff < a.tol && (!a.need_gs || gs < a.gs_tol))
             code = 1.0;
-          else if (k + 1 >= a.max_iter)
+          else if (kit + 1 >= a.max_iter)
             code = 2.0;
         }
         res_pool[bslot] = code;
@@ -945,7 +1176,7 @@ k_picard_resident(const __grid_constant__ RPlan plan, const __grid_constant__ Pi
       gs_last = res_pool[bslot + 4];
       const bool improved = res_pool[bslot + 5] != 0.0;
       __syncthreads();
-      iters = k + 1;
+      iters = kit + 1;
       GSB_PHASE(52);  // GS residual + decide
       if (blockIdx.x == 0 && threadIdx.x == 0) GSB_PHASE_COUNT(53);
       if (code == 3) {  // revert to the best state (newton_solver.py:518-532)
@@ -963,15 +1194,17 @@ k_picard_resident(const __grid_constant__ RPlan plan, const __grid_constant__ Pi
       }
     }
 
-    // ---- results
+    // ---- results: colour-split workspace -> dense outputs
     {
-      const double *fin = wpsi + (size_t)cur * n;
+      const double *fin = wpsi + (size_t)cur * planes;
       double *po = a.psi + (size_t)b * n;
       double *jo = a.jphi + (size_t)b * n;
-      for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        po[i] = fin[i];
-        jo[i] = wj[i];
-      }
+      for (int iz = warp; iz < nz; iz += nw)
+        for (int ir = lane; ir < nr; ir += 32) {
+          const int o = split_index(nz, hw, iz, ir);
+          po[iz * nr + ir] = fin[o];
+          jo[iz * nr + ir] = wj[o];
+        }
       if (threadIdx.x == 0 && a.summary) {
         double *o = a.summary + (size_t)b * 16;
         o[0] = (double)iters;
@@ -994,6 +1227,8 @@ k_picard_resident(const __grid_constant__ RPlan plan, const __grid_constant__ Pi
     }
     __syncthreads();
   }
+#undef GSB_SLOT_LOOP_BEGIN
+#undef GSB_SLOT_LOOP_END
 }
 
 }  // namespace gsb
@@ -1153,7 +1388,7 @@ static int picard_resident_launch(gsb_ctx *ctx, const gsb_picard_params *p, doub
   const RLevel &c1 = plan.lev[1];
   if (4 * c1.nz * c1.hw < nz * hw) return GSB_ESTATE;
   gsb_picard_ws *w = ctx->picard;
-  const size_t n = ctx->n, planes = (size_t)2 * nz * hw, per_cta = 4 * n + planes;
+  const size_t planes = (size_t)2 * nz * hw, per_cta = 5 * planes;
   const int grid = std::min(batch, ctx->num_sms);
   if (w->res_grid < grid) {
     if (w->res_ws) cudaFree(w->res_ws);
@@ -1172,8 +1407,8 @@ static int picard_resident_launch(gsb_ctx *ctx, const gsb_picard_params *p, doub
   a.hist = hist_dev;
   a.gs_hist = gs_hist_dev;
   a.ws_psi = w->res_ws;
-  a.ws_j = w->res_ws + (size_t)w->res_grid * 3 * n;
-  a.ws_src = a.ws_j + (size_t)w->res_grid * n;
+  a.ws_j = w->res_ws + (size_t)w->res_grid * 3 * planes;
+  a.ws_src = a.ws_j + (size_t)w->res_grid * planes;
   a.seedJ = w->seedJ;
   a.cf = w->cf;
   a.mr = w->mr;
