@@ -103,6 +103,11 @@ void gsb_destroy(gsb_ctx *ctx);
  * clip!=0 adds the +-1e250 clamp of _sor_step (fusion_kernel_iterative_solver.py:158). */
 int gsb_smooth(gsb_ctx *ctx, double *psi_dev, const double *src_dev, int batch, double omega,
                int n_sweeps, int clip, void *stream);
+/* Same, choosing the kernel: fuse = 0 launches one kernel per colour pass (48 B of DRAM traffic per
+ * point per sweep); fuse = 1..3 runs that many sweeps per pass over HBM with the temporally blocked
+ * kernel of gsb_sweep.cu (24 B per point per pass; identical results).  gsb_smooth uses fuse = 3. */
+int gsb_smooth_ex(gsb_ctx *ctx, double *psi_dev, const double *src_dev, int batch, double omega,
+                  int n_sweeps, int clip, int fuse, void *stream);
 /* a3: out-of-place toroidal Jacobi step with sanitise+clip (_jacobi_step, :54-95). */
 int gsb_jacobi(gsb_ctx *ctx, const double *psi_dev, const double *src_dev, double *out_dev,
                int batch, void *stream);

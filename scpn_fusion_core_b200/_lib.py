@@ -55,6 +55,7 @@ SIGNATURES = {
     "gsb_create": (c_int, [POINTER(c_void_p), c_int, c_int, _dp, _dp, c_double, c_double, c_int, c_int]),
     "gsb_destroy": (None, [c_void_p]),
     "gsb_smooth": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_double, c_int, c_int, c_void_p]),
+    "gsb_smooth_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_double, c_int, c_int, c_int, c_void_p]),
     "gsb_jacobi": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "gsb_residual": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "gsb_apply_operator": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),

@@ -101,6 +101,7 @@ static void free_levels(gsb_ctx *ctx) {
     if (l.tables) cudaFree(l.tables);
     if (l.d) cudaFree(l.d);
     if (l.e) cudaFree(l.e);
+    if (l.alt) cudaFree(l.alt);
   }
   ctx->levels.clear();
   ctx->planned_min_grid = -1;
@@ -289,6 +290,7 @@ void gsb_destroy(gsb_ctx *ctx) {
   if (ctx->counter) cudaFree(ctx->counter);
   if (ctx->mg_bc) cudaFree(ctx->mg_bc);
   if (ctx->split_src) cudaFree(ctx->split_src);
+  if (ctx->x_alt) cudaFree(ctx->x_alt);
   if (ctx->h_counter) cudaFreeHost(ctx->h_counter);
   delete ctx;
 }

@@ -282,6 +282,7 @@ struct gsb_level_dev {
   double *tables = nullptr;  // one allocation: a_e | a_w | r_safe | inv_r_safe
   double *d = nullptr;       // coarse right-hand side  [batch_cap][n]   (levels >= 1)
   double *e = nullptr;       // coarse correction       [batch_cap][n]   (levels >= 1)
+  double *alt = nullptr;     // ping-pong partner of the level's solution for out-of-place fused sweeps (lazy)
 };
 
 struct gsb_picard_ws;  // defined in gsb_picard.cu
@@ -296,6 +297,7 @@ struct gsb_ctx {
   int planned_min_grid = -1;
   int res_l0 = -1;          // first level of the shared-memory-resident V-cycle tail (n_levels = none)
   double *split_src = nullptr;  // [batch_cap][2*nz*hw] level-0 rhs in colour-split layout
+  double *x_alt = nullptr;      // [batch_cap][n] level-0 ping-pong partner for out-of-place fused sweeps (lazy)
   int num_sms = 148;
   std::vector<gsb_level_dev> levels;
   double *z_dev = nullptr;  // [nz]
@@ -321,6 +323,17 @@ int vcycle_launch(gsb_ctx *ctx, double *psi, size_t psi_stride, const double *sr
                   double omega, int pre, int post, const int *active, cudaStream_t st);
 int smooth_launch(const LevelGeom &g, double *psi, size_t stride, const double *src, size_t sstride,
                   int batch, double omega, int sweeps, int clip, const int *active, cudaStream_t st);
+// temporally blocked sweeps (gsb_sweep.cu): `sweeps` (1..3) full RB-SOR sweeps in one pass over HBM
+int sweep_fused_launch(const LevelGeom &g, const double *in, size_t istride, double *out, size_t ostride,
+                       const double *src, size_t sstride, int batch, double omega, int sweeps, int par_off,
+                       int num_sms, const int *active, cudaStream_t st);
+void sweep_fused_plan(int nz, int nr, int batch, int nst, int num_sms, int *strip_cols, int *band_rows,
+                      int *n_strips, int *n_bands);
+// n_sweeps sweeps of level `g` starting from `cur` (in place when one tile per equilibrium covers the
+// grid, otherwise ping-pong with `alt`); *result receives the buffer that holds the outcome.
+int smooth_fused(gsb_ctx *ctx, const LevelGeom &g, double *cur, double *alt, size_t stride, const double *src,
+                 size_t sstride, int batch, double omega, int n_sweeps, const int *active, cudaStream_t st,
+                 double **result);
 int jacobi_launch(const LevelGeom &g, const double *psi, const double *src, double *out, int batch,
                   const int *active, cudaStream_t st);
 int ring_save_launch(const double *f, size_t stride, double *ring, int nz, int nr, int batch,

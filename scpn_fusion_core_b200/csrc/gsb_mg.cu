@@ -60,6 +60,29 @@ int smooth_launch(const LevelGeom &g, double *psi, size_t stride, const double *
   return GSB_OK;
 }
 
+// Fused sweeps with the tile plan of gsb_sweep.cu.  Single tile per equilibrium: in place.
+// Otherwise out of place, ping-pong between `cur` and `alt`.
+int smooth_fused(gsb_ctx *ctx, const LevelGeom &g, double *cur, double *alt, size_t stride, const double *src,
+                 size_t sstride, int batch, double omega, int n_sweeps, const int *active, cudaStream_t st,
+                 double **result) {
+  *result = cur;
+  if (g.nz < 3 || g.nr < 3 || n_sweeps <= 0 || batch <= 0) return GSB_OK;
+  int remaining = n_sweeps;
+  while (remaining > 0) {
+    const int s = std::min(remaining, 3);
+    int sc, br, ns, nb;
+    sweep_fused_plan(g.nz, g.nr, batch, 2 * s, ctx->num_sms, &sc, &br, &ns, &nb);
+    const bool inplace = (ns == 1 && nb == 1);
+    double *dst = inplace ? *result : (*result == cur ? alt : cur);
+    GSB_REQUIRE(dst != nullptr, "smooth_fused: out-of-place sweep needs an alternate buffer");
+    int rc = sweep_fused_launch(g, *result, stride, dst, stride, src, sstride, batch, omega, s, 0, ctx->num_sms, active, st);
+    if (rc) return rc;
+    *result = dst;
+    remaining -= s;
+  }
+  return GSB_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // a3  Jacobi step  (fusion_kernel_iterative_solver.py:54-95): sanitised inputs, clipped output
 // ------------------------------------------------------------------------------------------
@@ -501,14 +524,40 @@ int vcycle_launch(gsb_ctx *ctx, double *psi, size_t psi_stride, const double *sr
   auto S = [&](int l) { return l == 0 ? src : (const double *)ctx->levels[l].d; };
   auto SS = [&](int l) { return l == 0 ? ctx->n : (size_t)ctx->levels[l].g.nz * ctx->levels[l].g.nr; };
   const int top = std::min(l0, L - 1);  // levels [0, top) are smoothed by streaming kernels
+  // ping-pong partners for out-of-place fused sweeps (multi-tile levels), allocated on first use
+  auto ALT = [&](int l, double **out) -> int {
+    const LevelGeom &g = ctx->levels[l].g;
+    int sc, br, ns, nb;
+    sweep_fused_plan(g.nz, g.nr, batch, 6, ctx->num_sms, &sc, &br, &ns, &nb);
+    *out = nullptr;
+    if (ns == 1 && nb == 1) return GSB_OK;
+    double **slot = l == 0 ? &ctx->x_alt : &ctx->levels[l].alt;
+    if (!*slot) GSB_CUDA(cudaMalloc(slot, (size_t)ctx->batch_cap * XS(l) * sizeof(double)));
+    *out = *slot;
+    return GSB_OK;
+  };
+  std::vector<double *> curv(L, nullptr);  // buffer holding each streaming level's solution after pre-smoothing
   for (int l = 0; l < top; ++l) {
     const LevelGeom &g = ctx->levels[l].g;
     const LevelGeom &c = ctx->levels[l + 1].g;
-    int rc = smooth_launch(g, X(l), XS(l), S(l), SS(l), batch, omega, pre, 0, active, st);
+    double *alt = nullptr;
+    int rc = ALT(l, &alt);
     if (rc) return rc;
+    if (alt && l == 0 && psi_stride != ctx->n) alt = nullptr;  // foreign stride: fall back to per-colour passes
+    double *cur = X(l);
+    {
+      int sc, br, ns, nb;
+      sweep_fused_plan(g.nz, g.nr, batch, 6, ctx->num_sms, &sc, &br, &ns, &nb);
+      if ((ns == 1 && nb == 1) || alt)
+        rc = smooth_fused(ctx, g, X(l), alt, XS(l), S(l), SS(l), batch, omega, pre, active, st, &cur);
+      else
+        rc = smooth_launch(g, X(l), XS(l), S(l), SS(l), batch, omega, pre, 0, active, st);
+    }
+    if (rc) return rc;
+    curv[l] = cur;
     const dim3 grd((c.nr + 31) / 32, (c.nz + 7) / 8, batch);
     const int split = (l + 1 == l0) ? 1 : 0;
-    k_residual_restrict<<<grd, blk, 0, st>>>(g, X(l), XS(l), S(l), SS(l), ctx->levels[l + 1].d, c.nz, c.nr, split, active);
+    k_residual_restrict<<<grd, blk, 0, st>>>(g, cur, XS(l), S(l), SS(l), ctx->levels[l + 1].d, c.nz, c.nr, split, active);
     GSB_LAUNCH_CHECK();
     if (l + 1 < L - 1 && l + 1 != l0)  // resident / base solve zero-initialise on chip
       GSB_CUDA(cudaMemsetAsync(ctx->levels[l + 1].e, 0, (size_t)batch * c.nz * c.nr * sizeof(double), st));
@@ -533,13 +582,25 @@ int vcycle_launch(gsb_ctx *ctx, double *psi, size_t psi_stride, const double *sr
   for (int l = top - 1; l >= 0; --l) {
     const LevelGeom &g = ctx->levels[l].g;
     const LevelGeom &c = ctx->levels[l + 1].g;
+    double *cur = curv[l] ? curv[l] : X(l);
     if (g.nz > 2 && g.nr > 2) {
       const dim3 grd((g.nr - 2 + 31) / 32, (g.nz - 2 + 7) / 8, batch);
-      k_prolong_add<<<grd, blk, 0, st>>>(ctx->levels[l + 1].e, c.nz, c.nr, X(l), XS(l), g.nz, g.nr, active);
+      k_prolong_add<<<grd, blk, 0, st>>>(ctx->levels[l + 1].e, c.nz, c.nr, cur, XS(l), g.nz, g.nr, active);
       GSB_LAUNCH_CHECK();
     }
-    int rc = smooth_launch(g, X(l), XS(l), S(l), SS(l), batch, omega, post, 0, active, st);
+    int rc;
+    double *fin = cur;
+    double *partner = (cur == X(l)) ? (l == 0 ? ctx->x_alt : ctx->levels[l].alt) : X(l);
+    int sc, br, ns, nb;
+    sweep_fused_plan(g.nz, g.nr, batch, 6, ctx->num_sms, &sc, &br, &ns, &nb);
+    const bool single = (ns == 1 && nb == 1);
+    if (single || (partner && !(l == 0 && psi_stride != ctx->n)))
+      rc = smooth_fused(ctx, g, cur, partner, XS(l), S(l), SS(l), batch, omega, post, active, st, &fin);
+    else
+      rc = smooth_launch(g, cur, XS(l), S(l), SS(l), batch, omega, post, 0, active, st);
     if (rc) return rc;
+    if (fin != X(l))  // odd number of out-of-place launches: bring the result home
+      GSB_CUDA(cudaMemcpyAsync(X(l), fin, (size_t)batch * XS(l) * sizeof(double), cudaMemcpyDeviceToDevice, st));
   }
   return GSB_OK;
 }
@@ -626,16 +687,43 @@ int gsb_debug_phase_cycles(long long *out64, int reset) {
   return picard_phase_read(out64, reset);  // the Picard translation unit has its own counters
 }
 
-int gsb_smooth(gsb_ctx *ctx, double *psi_dev, const double *src_dev, int batch, double omega,
-               int n_sweeps, int clip, void *stream) {
+int gsb_smooth_ex(gsb_ctx *ctx, double *psi_dev, const double *src_dev, int batch, double omega,
+                  int n_sweeps, int clip, int fuse, void *stream) {
   GSB_REQUIRE(ctx && psi_dev && src_dev, "gsb_smooth: NULL argument");
   GSB_REQUIRE(batch >= 1 && batch <= ctx->batch_cap, "gsb_smooth: batch outside [1, batch_cap]");
   GSB_REQUIRE(omega_ok(omega), "omega must be finite and satisfy 1.0 <= omega < 2.0");
+  GSB_REQUIRE(fuse >= 0 && fuse <= 3, "gsb_smooth_ex: fuse must be 0 (one launch per colour pass) or 1..3");
   GSB_CUDA(cudaSetDevice(ctx->device));
   int rc = ensure_plan(ctx, ctx->planned_min_grid < 0 ? 5 : ctx->planned_min_grid);
   if (rc) return rc;
-  return smooth_launch(ctx->levels[0].g, psi_dev, ctx->n, src_dev, ctx->n, batch, omega, n_sweeps,
-                       clip, nullptr, (cudaStream_t)stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  const LevelGeom &g = ctx->levels[0].g;
+  if (clip || fuse == 0 || g.nz < 3 || g.nr < 3)
+    return smooth_launch(g, psi_dev, ctx->n, src_dev, ctx->n, batch, omega, n_sweeps, clip, nullptr, st);
+  double *cur = psi_dev;
+  int remaining = n_sweeps;
+  while (remaining > 0) {
+    const int s = std::min(remaining, fuse);
+    int sc, br, ns, nb;
+    sweep_fused_plan(g.nz, g.nr, batch, 2 * s, ctx->num_sms, &sc, &br, &ns, &nb);
+    double *dst = cur;
+    if (!(ns == 1 && nb == 1)) {
+      if (!ctx->x_alt) GSB_CUDA(cudaMalloc(&ctx->x_alt, (size_t)ctx->batch_cap * ctx->n * sizeof(double)));
+      dst = (cur == psi_dev) ? ctx->x_alt : psi_dev;
+    }
+    rc = sweep_fused_launch(g, cur, ctx->n, dst, ctx->n, src_dev, ctx->n, batch, omega, s, 0, ctx->num_sms, nullptr, st);
+    if (rc) return rc;
+    cur = dst;
+    remaining -= s;
+  }
+  if (cur != psi_dev)
+    GSB_CUDA(cudaMemcpyAsync(psi_dev, cur, (size_t)batch * ctx->n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  return GSB_OK;
+}
+
+int gsb_smooth(gsb_ctx *ctx, double *psi_dev, const double *src_dev, int batch, double omega,
+               int n_sweeps, int clip, void *stream) {
+  return gsb_smooth_ex(ctx, psi_dev, src_dev, batch, omega, n_sweeps, clip, 3, stream);
 }
 
 int gsb_jacobi(gsb_ctx *ctx, const double *psi_dev, const double *src_dev, double *out_dev,

@@ -116,15 +116,18 @@ def _ctx(f: _Fields, r_grid, dr, dz, z_axis=None):
     return D.get_context(f.nz, f.nr, _r_row(r_grid, f.nz, f.nr), z_axis, float(dr), float(dz), f.B, f.device)
 
 
-def mg_smooth(psi, source, r_grid, dr: float, dz: float, omega: float, n_sweeps: int):
-    """multigrid_solve.py:148-208.  NumPy input is updated in place like the reference."""
+def mg_smooth(psi, source, r_grid, dr: float, dz: float, omega: float, n_sweeps: int, *, fuse: int = 3):
+    """multigrid_solve.py:148-208.  NumPy input is updated in place like the reference.
+
+    ``fuse`` (not in the reference) selects the kernel: 0 = one launch per colour pass, 1..3 = that
+    many sweeps per pass over HBM (temporally blocked, identical results; default 3)."""
     omega = validate_sor_omega(omega)
     f = _Fields(psi)
     ctx = _ctx(f, r_grid, dr, dz)
     p = f.dev(psi, copy=False)
     s = f.dev(source, copy=False)
-    _lib.check(ctx.lib.gsb_smooth(ctx.handle, D.ptr(p), D.ptr(s), f.B, omega, int(n_sweeps), 0, D.stream_ptr()),
-               "gsb_smooth")
+    _lib.check(ctx.lib.gsb_smooth_ex(ctx.handle, D.ptr(p), D.ptr(s), f.B, omega, int(n_sweeps), 0, int(fuse),
+                                     D.stream_ptr()), "gsb_smooth")
     if f.torch_in:
         if p.data_ptr() != psi.data_ptr():
             psi.copy_(p.reshape(psi.shape))
