@@ -223,6 +223,29 @@ int gsb_wall_flux(gsb_ctx *ctx, const double *m_dev, const double *jphi_dev, dou
 int gsb_wall_scatter(gsb_ctx *ctx, const double *wall_dev, double *bc_dev, int accumulate, int batch,
                      void *stream);
 
+/* --- slab operators: one large grid split into Z-row slabs, one process per GPU ------------- */
+/* (the reference's only decomposition code for this path is fusion-core/src/mpi_domain.rs:48-965,
+ * an additive-Schwarz scaffold; these keep exact RB-SOR instead)
+ * A slab context is gsb_create(rows_loc, nr, r_row_of_the_level, NULL, dr_level, dz_level, 1, dev):
+ * the local array [rows_loc][nr] = halo rows + owned rows + halo rows.  Host code exchanges halos. */
+/* 1 if `sweeps` fused sweeps of this local array run as a single tile (in-place allowed). */
+int gsb_slab_single_tile(gsb_ctx *ctx, int sweeps);
+/* sweeps (1..3) RB-SOR sweeps of the local array in one pass; rows 0 and rows_loc-1 are fixed.
+ * par_off = global row index of local row 0 (colour parity).  Owned rows are exact when at least
+ * 2*sweeps valid halo rows surround them (or the array edge is the true wall). */
+int gsb_slab_smooth(gsb_ctx *ctx, const double *in_dev, double *out_dev, const double *src_dev, double omega,
+                    int sweeps, int par_off, void *stream);
+/* coarse local rows [ci0,ci1) of dc = full weighting of -(L x - src); fine local row of coarse
+ * local row I is 2*I + roff; coarse column walls get 0. */
+int gsb_slab_residual_restrict(gsb_ctx *fine, const double *x_dev, const double *src_dev, double *dc_dev,
+                               int nzc_loc, int nrc, int roff, int ci0, int ci1, void *stream);
+/* x[fine local rows fi0..fi1), interior columns] += bilinear prolongation of ec. */
+int gsb_slab_prolong_add(gsb_ctx *fine, const double *ec_dev, int nzc_loc, int nrc, double *x_dev, int roff,
+                         int fi0, int fi1, void *stream);
+/* *out_dev = max(*out_dev, max |L x - src| over local rows [row0,row1), interior columns). */
+int gsb_slab_residual_linf(gsb_ctx *ctx, const double *x_dev, const double *src_dev, int row0, int row1,
+                           double *out_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -71,6 +71,12 @@ SIGNATURES = {
     "gsb_picard_solve": (c_int, [c_void_p, POINTER(gsb_picard_params), c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "gsb_picard_last_launched_iterations": (c_int, [c_void_p]),
+    "gsb_slab_single_tile": (c_int, [c_void_p, c_int]),
+    "gsb_slab_smooth": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_int, c_int, c_void_p]),
+    "gsb_slab_residual_restrict": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                           c_void_p]),
+    "gsb_slab_prolong_add": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "gsb_slab_residual_linf": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "gsb_b_field": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "gsb_green_table": (c_int, [c_void_p, _dp, c_int, c_int, c_void_p, c_void_p]),
     "gsb_coil_flux": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),

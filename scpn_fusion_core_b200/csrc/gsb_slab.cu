@@ -1,0 +1,169 @@
+// gsb_slab.cu - operators on a Z-row slab of one large grid (single-grid domain
+// decomposition, one process per GPU).  A slab is a local array [rows_loc][nr] = halo rows + owned
+// rows + halo rows of a level whose global shape is 2^k+1 in Z; the host side
+// (scpn_fusion_core_b200/slab.py) exchanges halo rows between neighbouring ranks with NCCL and
+// calls these entry points on its own rows.  Every kernel uses the same point functions as the
+// single-GPU path, so a slab solve is bit-identical to the single-GPU solve:
+//   * smoothing: the temporally blocked sweep of gsb_sweep.cu on the local array with the global
+//     row offset as colour-parity offset; with h >= 2*sweeps halo rows the owned rows are exact;
+//   * residual + full weighting, prolongation + add: one thread per point with a row offset between
+//     the local fine and coarse indices (fine local row = 2 * coarse local row + roff).
+#include "gsb_internal.cuh"
+
+namespace gsb {
+
+// coarse local rows [ci0, ci1), all coarse columns; column walls get 0 (multigrid_solve.py:303-306)
+__global__ void __launch_bounds__(256)
+k_slab_residual_restrict(LevelGeom g, const double *__restrict__ psi, const double *__restrict__ src,
+                         double *__restrict__ dc, int nrc, int roff, int ci0, int ci1) {
+  const int J = blockIdx.x * blockDim.x + threadIdx.x;
+  const int I = ci0 + blockIdx.y * blockDim.y + threadIdx.y;
+  if (I >= ci1 || J >= nrc) return;
+  double v = 0.0;
+  if (J > 0 && J < nrc - 1) {
+    double d[3][3];
+#pragma unroll
+    for (int a = -1; a <= 1; ++a)
+#pragma unroll
+      for (int c = -1; c <= 1; ++c) {
+        const int iz = 2 * I + roff + a, ir = 2 * J + c;
+        const double *q = psi + (size_t)iz * g.nr + ir;
+        const double r = dsub(gs_apply(g, ir, q[0], q[1], q[-1], q[-g.nr], q[g.nr]), src[(size_t)iz * g.nr + ir]);
+        d[a + 1][c + 1] = -r;
+      }
+    v = fw9(d[1][1], d[0][1], d[2][1], d[1][0], d[1][2], d[0][0], d[0][2], d[2][0], d[2][2]);
+  }
+  dc[(size_t)I * nrc + J] = v;
+}
+
+// psi[fine local rows fi0..fi1) interior columns] += P e   (prolongate_bilinear, odd sizes)
+__global__ void __launch_bounds__(256)
+k_slab_prolong_add(const double *__restrict__ ec, int nrc, double *__restrict__ psi, int nrf, int roff, int fi0,
+                   int fi1) {
+  const int ir = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+  const int lf = fi0 + blockIdx.y * blockDim.y + threadIdx.y;
+  if (lf >= fi1 || ir >= nrf - 1) return;
+  const int v = lf - roff;  // = 2 * coarse local row (+1 for rows between two coarse rows)
+  const int I = v >> 1, J = ir >> 1;
+  const bool ze = (v & 1) == 0, re = (ir & 1) == 0;
+  const double *p = ec + (size_t)I * nrc + J;
+  double out;
+  if (ze && re)
+    out = p[0];
+  else if (ze)
+    out = dmul(0.5, dadd(p[0], p[1]));
+  else if (re)
+    out = dmul(0.5, dadd(p[0], p[nrc]));
+  else
+    out = dmul(0.25, dadd(dadd(dadd(p[0], p[nrc]), p[1]), p[nrc + 1]));
+  double *q = psi + (size_t)lf * nrf + ir;
+  q[0] = dadd(q[0], out);
+}
+
+// max |L psi - src| over local rows [row0,row1), interior columns; out accumulates with atomicMax on
+// the bit pattern (non-negative doubles order like unsigned integers) - order independent
+__global__ void __launch_bounds__(256)
+k_slab_residual_linf(LevelGeom g, const double *__restrict__ psi, const double *__restrict__ src, int row0, int row1,
+                     unsigned long long *__restrict__ out) {
+  __shared__ double sh[32];
+  double m = 0.0;
+  const int ncol = g.nr - 2;
+  const long long total = (long long)(row1 - row0) * ncol;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int iz = row0 + (int)(i / ncol), ir = 1 + (int)(i % ncol);
+    const double *q = psi + (size_t)iz * g.nr + ir;
+    const double r = dsub(gs_apply(g, ir, q[0], q[1], q[-1], q[-g.nr], q[g.nr]), src[(size_t)iz * g.nr + ir]);
+    const double ar = fabs(r);
+    if (ar > m || isnan(ar)) m = ar;  // a NaN residual must surface (np.max propagates NaN)
+  }
+  // block_max uses fmax (drops NaN): carry a NaN flag alongside
+  const int anynan = __syncthreads_or(isnan(m) ? 1 : 0);
+  m = block_max(isnan(m) ? 0.0 : m, sh);
+  if (threadIdx.x == 0) {
+    if (anynan)
+      atomicMax(out, 0x7ff8000000000000ULL);
+    else
+      atomicMax(out, (unsigned long long)__double_as_longlong(m));
+  }
+}
+
+static int slab_plan(gsb_ctx *ctx) {
+  // a slab context has exactly one level: the local array itself
+  return ensure_plan(ctx, 1 << 30);
+}
+
+}  // namespace gsb
+
+using namespace gsb;
+
+extern "C" {
+
+int gsb_slab_single_tile(gsb_ctx *ctx, int sweeps) {
+  if (!ctx || sweeps < 1 || sweeps > 3) return 0;
+  int sc, br, ns, nb;
+  sweep_fused_plan(ctx->nz, ctx->nr, 1, 2 * sweeps, ctx->num_sms, &sc, &br, &ns, &nb);
+  return (ns == 1 && nb == 1) ? 1 : 0;
+}
+
+int gsb_slab_smooth(gsb_ctx *ctx, const double *in_dev, double *out_dev, const double *src_dev, double omega,
+                    int sweeps, int par_off, void *stream) {
+  GSB_REQUIRE(ctx && in_dev && out_dev && src_dev, "gsb_slab_smooth: NULL argument");
+  GSB_REQUIRE(sweeps >= 1 && sweeps <= 3, "gsb_slab_smooth: 1..3 sweeps per call");
+  GSB_REQUIRE(std::isfinite(omega) && omega >= 1.0 && omega < 2.0, "omega must be finite and satisfy 1.0 <= omega < 2.0");
+  GSB_CUDA(cudaSetDevice(ctx->device));
+  int rc = slab_plan(ctx);
+  if (rc) return rc;
+  return sweep_fused_launch(ctx->levels[0].g, in_dev, ctx->n, out_dev, ctx->n, src_dev, ctx->n, 1, omega, sweeps,
+                            par_off & 1, ctx->num_sms, nullptr, (cudaStream_t)stream);
+}
+
+int gsb_slab_residual_restrict(gsb_ctx *fine, const double *x_dev, const double *src_dev, double *dc_dev,
+                               int nzc_loc, int nrc, int roff, int ci0, int ci1, void *stream) {
+  GSB_REQUIRE(fine && x_dev && src_dev && dc_dev, "gsb_slab_residual_restrict: NULL argument");
+  GSB_REQUIRE(nrc == (fine->nr + 1) / 2 && (fine->nr & 1), "gsb_slab_residual_restrict: needs an odd fine width");
+  GSB_REQUIRE(ci0 >= 0 && ci1 <= nzc_loc && ci0 <= ci1, "gsb_slab_residual_restrict: bad coarse row range");
+  if (ci0 < ci1)
+    GSB_REQUIRE(2 * ci0 + roff - 2 >= 0 && 2 * (ci1 - 1) + roff + 2 <= fine->nz - 1,
+                "gsb_slab_residual_restrict: fine halo rows missing");
+  GSB_CUDA(cudaSetDevice(fine->device));
+  int rc = slab_plan(fine);
+  if (rc) return rc;
+  if (ci0 == ci1) return GSB_OK;
+  const dim3 blk(32, 8, 1), grd((nrc + 31) / 32, (ci1 - ci0 + 7) / 8, 1);
+  k_slab_residual_restrict<<<grd, blk, 0, (cudaStream_t)stream>>>(fine->levels[0].g, x_dev, src_dev, dc_dev, nrc, roff, ci0, ci1);
+  GSB_LAUNCH_CHECK();
+  return GSB_OK;
+}
+
+int gsb_slab_prolong_add(gsb_ctx *fine, const double *ec_dev, int nzc_loc, int nrc, double *x_dev, int roff,
+                         int fi0, int fi1, void *stream) {
+  GSB_REQUIRE(fine && ec_dev && x_dev, "gsb_slab_prolong_add: NULL argument");
+  GSB_REQUIRE(nrc == (fine->nr + 1) / 2 && (fine->nr & 1), "gsb_slab_prolong_add: needs an odd fine width");
+  GSB_REQUIRE(fi0 >= 0 && fi1 <= fine->nz && fi0 <= fi1, "gsb_slab_prolong_add: bad fine row range");
+  if (fi0 < fi1)
+    GSB_REQUIRE(fi0 - roff >= 0 && ((fi1 - 1 - roff + 1) >> 1) <= nzc_loc - 1, "gsb_slab_prolong_add: coarse halo rows missing");
+  GSB_CUDA(cudaSetDevice(fine->device));
+  if (fi0 == fi1 || fine->nr < 3) return GSB_OK;
+  const dim3 blk(32, 8, 1), grd((fine->nr - 2 + 31) / 32, (fi1 - fi0 + 7) / 8, 1);
+  k_slab_prolong_add<<<grd, blk, 0, (cudaStream_t)stream>>>(ec_dev, nrc, x_dev, fine->nr, roff, fi0, fi1);
+  GSB_LAUNCH_CHECK();
+  return GSB_OK;
+}
+
+int gsb_slab_residual_linf(gsb_ctx *ctx, const double *x_dev, const double *src_dev, int row0, int row1,
+                           double *out_dev, void *stream) {
+  GSB_REQUIRE(ctx && x_dev && src_dev && out_dev, "gsb_slab_residual_linf: NULL argument");
+  GSB_REQUIRE(row0 >= 1 && row1 <= ctx->nz - 1 && row0 <= row1, "gsb_slab_residual_linf: rows must be interior to the local array");
+  GSB_CUDA(cudaSetDevice(ctx->device));
+  int rc = slab_plan(ctx);
+  if (rc) return rc;
+  if (row0 == row1 || ctx->nr < 3) return GSB_OK;
+  const long long total = (long long)(row1 - row0) * (ctx->nr - 2);
+  const int blocks = (int)std::min<long long>((total + 255) / 256, 4LL * ctx->num_sms);
+  k_slab_residual_linf<<<blocks, 256, 0, (cudaStream_t)stream>>>(ctx->levels[0].g, x_dev, src_dev, row0, row1,
+                                                                 reinterpret_cast<unsigned long long *>(out_dev));
+  GSB_LAUNCH_CHECK();
+  return GSB_OK;
+}
+
+}  // extern "C"

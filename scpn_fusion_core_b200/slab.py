@@ -1,0 +1,358 @@
+"""Slab-decomposed multigrid_solve: ONE large (R,Z) grid split into Z-row slabs, one process per GPU.
+
+The reference solves a single grid on one device (``multigrid_solve``, ``multigrid_solve.py:352-463``);
+its only decomposition code for this path is the additive-Schwarz scaffold of
+``scpn-fusion-rs/crates/fusion-core/src/mpi_domain.rs:48-965`` (threads + serial copies, not the same
+iteration).  This module keeps the reference's iteration exactly - a slab solve is bit-identical to
+the single-GPU solve - and exchanges halo rows between neighbouring ranks:
+
+* rank r owns global rows [r*R, (r+1)*R) of every distributed level (the last rank also owns the
+  wall row); local arrays carry ``halo`` rows on each inner side;
+* smoothing = temporally blocked RB-SOR sweeps on the local array (``gsb_slab_smooth``): one halo
+  exchange of 2*sweeps rows per smoothing phase instead of one row per colour pass;
+* residual + full weighting and prolongation + add act on owned rows with one-/two-row halos;
+* once a level has fewer than ``min_rows`` rows per rank its right-hand side is all-gathered and
+  the rest of the V-cycle runs replicated on every rank (no scatter needed afterwards);
+* the convergence norm is an all-reduce(MAX) of one double per cycle.
+
+Communication goes through ``torch.distributed`` point-to-point ops (NCCL over NVLink on the GPU
+box; with the gloo backend halo rows are staged through host memory, which is how the two-rank
+tests run).  The compute backend is injected (``ops``): ``CudaSlabOps`` drives libgsb200; the CPU
+tests inject an oracle-backed implementation to check the orchestration without a GPU.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Any
+
+import numpy as np
+
+from . import _lib
+
+
+@dataclass
+class SlabLevel:
+    """One distributed level as seen by one rank."""
+    nz: int        # global rows
+    nr: int        # columns
+    g0: int        # first owned global row
+    g1: int        # one past the last owned global row
+    h_top: int     # halo rows above / below the owned rows
+    h_bot: int
+    dr: float
+    dz: float
+    r_row: np.ndarray
+
+    @property
+    def rows_loc(self) -> int:
+        return self.h_top + (self.g1 - self.g0) + self.h_bot
+
+    @property
+    def row0(self) -> int:
+        """global row index of local row 0"""
+        return self.g0 - self.h_top
+
+    def loc(self, g: int) -> int:
+        return g - self.row0
+
+
+def plan_slab_levels(nz: int, nr: int, r_min: float, r_max: float, z_min: float, z_max: float, world: int,
+                     rank: int, *, halo: int = 6, min_rows: int = 32, min_grid: int = 5) -> tuple[list[SlabLevel], dict]:
+    """Row partition of every distributed level plus the geometry of the first gathered level.
+
+    Needs nz = 2^p + 1 rows with (nz-1) divisible by world; a level stays distributed while it has at
+    least ``min_rows`` (and an even number of) rows per rank and the reference's recursion continues.
+    """
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("bad rank/world")
+    if (nz - 1) % world or (nz - 1) & (nz - 2) or (nr - 1) & (nr - 2):
+        raise ValueError("slab mode needs a (2^p+1) x (2^q+1) grid and (nz-1) divisible by the world size")
+    lib = _lib.load()
+    dp = ctypes.POINTER(ctypes.c_double)
+    r_axis = np.linspace(r_min, r_max, nr)
+    z_axis = np.linspace(z_min, z_max, nz)
+    dr, dz = float(r_axis[1] - r_axis[0]), float(z_axis[1] - z_axis[0])  # multigrid_solve.py:431-432
+
+    def tables(level: int):
+        n_r = (nr - 1) // (1 << level) + 1
+        r = np.zeros(n_r)
+        sc = np.zeros(4)
+        n = lib.gsb_plan_level_tables(nz, nr, r_axis.ctypes.data_as(dp), dr, dz, min_grid, level,
+                                      r.ctypes.data_as(dp), None, None, sc.ctypes.data_as(dp))
+        if n != n_r:
+            raise _lib.GsbError("gsb_plan_level_tables: unexpected level width")
+        r[0], r[-1] = r_axis[0], r_axis[-1]  # wall columns are injected (multigrid_solve.py:93-98)
+        return r, float(sc[0]), float(sc[1])
+
+    levels: list[SlabLevel] = []
+    lev = 0
+    nz_l, nr_l = nz, nr
+    while True:
+        rows = (nz_l - 1) // world
+        stop = min_grid >= nz_l or min_grid >= nr_l  # the reference's base case (multigrid_solve.py:292)
+        if stop or rows < max(min_rows, 2 * halo) or rows % 2:
+            break
+        r_row, dr_l, dz_l = tables(lev)
+        g0 = rank * rows
+        g1 = (rank + 1) * rows + (1 if rank == world - 1 else 0)
+        levels.append(SlabLevel(nz_l, nr_l, g0, g1, 0 if rank == 0 else halo, 0 if rank == world - 1 else halo,
+                                dr_l, dz_l, r_row))
+        nz_l, nr_l = (nz_l + 1) // 2, (nr_l + 1) // 2
+        lev += 1
+    r_row, dr_l, dz_l = tables(lev)
+    gathered = {"level": lev, "nz": nz_l, "nr": nr_l, "r_row": r_row, "dr": dr_l, "dz": dz_l,
+                "rows_per_rank": (nz_l - 1) // world}
+    return levels, gathered
+
+
+class CudaSlabOps:
+    """Compute backend on one GPU: libgsb200 slab entry points + torch CUDA tensors as buffers."""
+
+    def __init__(self, device: int):
+        from . import _device as D
+        self.D = D
+        self.device = device
+        self.torch = D.torch_mod()
+        self._ctx: dict = {}
+        self._alt: dict = {}
+
+    def zeros(self, shape):
+        return self.D.zeros(shape, self.device)
+
+    def from_numpy(self, a):
+        return self.D.to_device(a, self.device)
+
+    def to_numpy(self, t):
+        return t.cpu().numpy()
+
+    def _context(self, L: SlabLevel):
+        key = (L.nz, L.nr, L.rows_loc, L.dr, L.dz)
+        if key not in self._ctx:
+            self._ctx[key] = self.D.Context(L.rows_loc, L.nr, L.r_row, None, L.dr, L.dz, 1, self.device)
+        return self._ctx[key]
+
+    def smooth(self, L: SlabLevel, x, f, omega: float, sweeps: int):
+        """``sweeps`` RB-SOR sweeps of the local array; returns the tensor holding the result."""
+        D = self.D
+        ctx = self._context(L)
+        st = D.stream_ptr()
+        cur = x
+        left = sweeps
+        while left > 0:
+            s = min(left, 3)
+            if ctx.lib.gsb_slab_single_tile(ctx.handle, s):
+                dst = cur
+            else:  # out of place: write into a cached buffer of this shape that is not the input
+                pool = self._alt.setdefault((L.rows_loc, L.nr), [])
+                dst = next((b for b in pool if b.data_ptr() != cur.data_ptr()), None)
+                if dst is None:
+                    dst = D.empty(tuple(x.shape), self.device)
+                    pool.append(dst)
+            _lib.check(ctx.lib.gsb_slab_smooth(ctx.handle, D.ptr(cur), D.ptr(dst), D.ptr(f), omega, s, L.row0, st),
+                       "gsb_slab_smooth")
+            cur = dst
+            left -= s
+        return cur  # may be a pooled buffer: callers rebind (the input tensor is then scratch)
+
+    def residual_restrict(self, L: SlabLevel, C: SlabLevel | None, x, f, d, roff: int, ci0: int, ci1: int):
+        D = self.D
+        ctx = self._context(L)
+        _lib.check(ctx.lib.gsb_slab_residual_restrict(ctx.handle, D.ptr(x), D.ptr(f), D.ptr(d), int(d.shape[0]),
+                                                      int(d.shape[1]), roff, ci0, ci1, D.stream_ptr()),
+                   "gsb_slab_residual_restrict")
+
+    def prolong_add(self, L: SlabLevel, x, e, roff: int, fi0: int, fi1: int):
+        D = self.D
+        ctx = self._context(L)
+        _lib.check(ctx.lib.gsb_slab_prolong_add(ctx.handle, D.ptr(e), int(e.shape[0]), int(e.shape[1]), D.ptr(x), roff,
+                                                fi0, fi1, D.stream_ptr()), "gsb_slab_prolong_add")
+
+    def residual_linf(self, L: SlabLevel, x, f, row0: int, row1: int) -> float:
+        D = self.D
+        ctx = self._context(L)
+        out = D.zeros((1,), self.device)
+        _lib.check(ctx.lib.gsb_slab_residual_linf(ctx.handle, D.ptr(x), D.ptr(f), row0, row1, D.ptr(out),
+                                                  D.stream_ptr()), "gsb_slab_residual_linf")
+        return float(out.item())
+
+    def coarse_vcycle(self, G: dict, d_full, omega: float, pre: int, post: int, min_grid: int):
+        """The replicated tail of the V-cycle on the gathered level (zero initial guess)."""
+        from . import multigrid_solve as mg
+        import importlib
+        mgm = importlib.import_module(__package__ + ".multigrid_solve")
+        rg = np.tile(G["r_row"], (G["nz"], 1))
+        x0 = self.torch.zeros_like(d_full)
+        return mgm.multigrid_vcycle(x0, d_full, rg, G["dr"], G["dz"], omega=omega, pre_smooth=pre, post_smooth=post,
+                                    min_grid=min_grid)
+
+
+class SlabComm:
+    """Halo exchange / gather / max-reduce over a torch.distributed process group (NCCL or gloo)."""
+
+    def __init__(self, rank: int, world: int, group=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank, self.world, self.group = rank, world, group
+        self.backend = dist.get_backend(group) if world > 1 else "none"
+        self.bytes_sent = 0
+        self.messages = 0
+
+    def _stage(self, t):
+        # gloo cannot move CUDA tensors point-to-point: stage through host memory
+        return t.cpu() if (self.backend == "gloo" and t.is_cuda) else t
+
+    def exchange(self, x, L: SlabLevel, k: int) -> None:
+        """Fill the innermost k halo rows on both sides of x from the neighbours' owned rows."""
+        if self.world == 1 or k == 0:
+            return
+        dist = self.dist
+        ops, recvs = [], []
+        own0, own1 = L.h_top, L.h_top + (L.g1 - L.g0)
+        if L.h_top:  # upper neighbour: send my first k owned rows, receive its last k owned rows
+            send = self._stage(x[own0:own0 + k].contiguous())
+            recv = self.torch.empty_like(send)
+            ops += [dist.P2POp(dist.isend, send, self.rank - 1, self.group), dist.P2POp(dist.irecv, recv, self.rank - 1, self.group)]
+            recvs.append((recv, slice(own0 - k, own0)))
+        if L.h_bot:
+            send = self._stage(x[own1 - k:own1].contiguous())
+            recv = self.torch.empty_like(send)
+            ops += [dist.P2POp(dist.isend, send, self.rank + 1, self.group), dist.P2POp(dist.irecv, recv, self.rank + 1, self.group)]
+            recvs.append((recv, slice(own1, own1 + k)))
+        for r in dist.batch_isend_irecv(ops):
+            r.wait()
+        for recv, sl in recvs:
+            x[sl].copy_(recv)
+            self.bytes_sent += recv.numel() * 8
+            self.messages += 1
+
+    def gather_rows(self, owned, rows_per_rank: int, nz: int):
+        """All-gather the owned rows of a level into the full (nz, nr) array on every rank."""
+        if self.world == 1:
+            return owned
+        t = self._stage(owned[:rows_per_rank].contiguous())
+        parts = [self.torch.empty_like(t) for _ in range(self.world)]
+        self.dist.all_gather(parts, t, group=self.group)
+        last = self._stage(owned[rows_per_rank:rows_per_rank + 1].contiguous()) if self.rank == self.world - 1 \
+            else self.torch.empty((1, owned.shape[1]), dtype=owned.dtype, device=t.device)
+        self.dist.broadcast(last, src=self._global_rank(self.world - 1), group=self.group)
+        full = self.torch.cat(parts + [last], dim=0)
+        assert full.shape[0] == nz
+        return full.to(owned.device)
+
+    def _global_rank(self, group_rank: int) -> int:
+        return self.dist.get_global_rank(self.group, group_rank) if self.group is not None else group_rank
+
+    def max(self, v: float) -> float:
+        if self.world == 1:
+            return v
+        t = self.torch.tensor([v], dtype=self.torch.float64)
+        if self.backend == "nccl":
+            t = t.cuda()
+        # NaN must win like np.max: reduce a NaN flag alongside
+        flag = self.torch.tensor([1.0 if v != v else 0.0], dtype=self.torch.float64, device=t.device)
+        t = self.torch.nan_to_num(t, nan=0.0)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
+        self.dist.all_reduce(flag, op=self.dist.ReduceOp.MAX, group=self.group)
+        return float("nan") if flag.item() > 0 else float(t.item())
+
+
+class SlabMultigrid:
+    """``multigrid_solve`` for one rank's slab.  API mirrors ``multigrid_solve.py:352`` except that
+    ``source`` / ``psi_bc`` are this rank's OWNED rows (``owned_rows()``) of the global arrays."""
+
+    def __init__(self, nz: int, nr: int, r_min: float, r_max: float, z_min: float, z_max: float, comm: SlabComm,
+                 ops: Any, *, halo: int = 6, min_rows: int = 32, omega: float = 1.0, pre_smooth: int = 3,
+                 post_smooth: int = 3, min_grid: int = 5):
+        if halo < 2 * min(3, max(pre_smooth, post_smooth)):
+            raise ValueError("halo must cover 2 rows per fused sweep (up to 3 sweeps per pass)")
+        self.comm, self.ops = comm, ops
+        self.omega, self.pre, self.post, self.min_grid, self.halo = omega, pre_smooth, post_smooth, min_grid, halo
+        self.levels, self.gathered = plan_slab_levels(nz, nr, r_min, r_max, z_min, z_max, comm.world, comm.rank,
+                                                      halo=halo, min_rows=min_rows, min_grid=min_grid)
+        if not self.levels:
+            raise ValueError("grid too small for a slab decomposition at this world size (use multigrid_solve)")
+        self.nz, self.nr = nz, nr
+
+    def owned_rows(self) -> tuple[int, int]:
+        L = self.levels[0]
+        return L.g0, L.g1
+
+    # ---- one V-cycle on distributed level l; x and f are local arrays (halo rows included) ----
+    def _vcycle(self, l: int, x, f):
+        L = self.levels[l]
+        ops, comm = self.ops, self.comm
+        own0, own1 = L.h_top, L.h_top + (L.g1 - L.g0)
+        comm.exchange(x, L, self.halo)
+        x = ops.smooth(L, x, f, self.omega, self.pre)
+        comm.exchange(x, L, 2)
+        nzc, nrc = (L.nz + 1) // 2, (L.nr + 1) // 2
+        dist_next = l + 1 < len(self.levels)
+        if dist_next:
+            C = self.levels[l + 1]
+            c_rows, c_row0, c_htop = C.rows_loc, C.row0, C.h_top
+            cg0, cg1 = C.g0, C.g1
+        else:
+            G = self.gathered
+            rpr = G["rows_per_rank"]
+            cg0 = comm.rank * rpr
+            cg1 = (comm.rank + 1) * rpr + (1 if comm.rank == comm.world - 1 else 0)
+            c_htop = 0
+            c_rows, c_row0 = cg1 - cg0, cg0
+        roff = 2 * c_row0 - L.row0  # fine local row of coarse local row I is 2*I + roff
+        d = ops.zeros((c_rows, nrc))
+        ci0, ci1 = max(1, cg0) - c_row0, min(nzc - 1, cg1) - c_row0  # owned coarse rows that are not global walls
+        ops.residual_restrict(L, None, x, f, d, roff, ci0, ci1)
+        if dist_next:
+            comm.exchange(d, C, self.halo)  # the halo rows are re-smoothed redundantly and need their rhs
+            e = ops.zeros((c_rows, nrc))
+            e = self._vcycle(l + 1, e, d)
+            comm.exchange(e, C, 1)
+            e_loc, e_row0 = e, c_row0
+        else:
+            d_full = comm.gather_rows(d, rpr, nzc)
+            e_full = ops.coarse_vcycle(self.gathered, d_full, self.omega, self.pre, self.post, self.min_grid)
+            lo, hi = max(0, cg0 - 1), min(nzc, cg1 + 1)
+            e_loc, e_row0 = e_full[lo:hi].contiguous(), lo
+            roff = 2 * e_row0 - L.row0
+        fi0, fi1 = max(1, L.g0) - L.row0, min(L.nz - 1, L.g1) - L.row0  # owned fine rows that are not global walls
+        ops.prolong_add(L, x, e_loc, roff, fi0, fi1)
+        comm.exchange(x, L, self.halo)
+        x = ops.smooth(L, x, f, self.omega, self.post)
+        return x
+
+    def solve(self, source_owned, psi_bc_owned, *, tol: float = 1e-6, max_cycles: int = 500):
+        """Returns (psi_owned_rows, residual_linf, n_cycles, converged) - residual/cycles/converged are
+        global (identical on every rank), like multigrid_solve.py:352-463."""
+        if not (np.isfinite(tol) and tol > 0):
+            raise ValueError("tol must be finite and > 0")
+        if max_cycles < 1:
+            raise ValueError("max_cycles must be >= 1")
+        L = self.levels[0]
+        ops, comm = self.ops, self.comm
+        n_own = L.g1 - L.g0
+        own = slice(L.h_top, L.h_top + n_own)
+        f = ops.zeros((L.rows_loc, L.nr))
+        bc = ops.zeros((L.rows_loc, L.nr))
+        f[own] = ops.from_numpy(np.asarray(source_owned, dtype=np.float64)) if isinstance(source_owned, np.ndarray) else source_owned
+        bc[own] = ops.from_numpy(np.asarray(psi_bc_owned, dtype=np.float64)) if isinstance(psi_bc_owned, np.ndarray) else psi_bc_owned
+        comm.exchange(f, L, self.halo)
+        x = bc.clone()
+        r0, r1 = max(1, L.g0) - L.row0, min(L.nz - 1, L.g1) - L.row0
+        comm.exchange(x, L, 1)
+        residual = comm.max(ops.residual_linf(L, x, f, r0, r1))
+        cycles = 0
+        while not residual < tol and cycles < max_cycles:
+            x = self._vcycle(0, x, f)
+            # Dirichlet ring (multigrid_solve.py:437-441,458)
+            x[own, 0] = bc[own, 0]
+            x[own, -1] = bc[own, -1]
+            if L.g0 == 0:
+                x[L.h_top] = bc[L.h_top]
+            if L.g1 == L.nz:
+                x[L.h_top + n_own - 1] = bc[L.h_top + n_own - 1]
+            comm.exchange(x, L, 1)
+            residual = comm.max(ops.residual_linf(L, x, f, r0, r1))
+            cycles += 1
+        return x[own], residual, cycles, bool(residual < tol)
