@@ -6,7 +6,9 @@ A drop-in for the equilibrium entry points of anulum/scpn-fusion-core
 behind a C ABI (``include/gsb200.h``).  See DESIGN.md / INTEGRATION.md.
 """
 from . import _lib  # noqa: F401
-from .fusion_kernel import BatchedFusionKernel, CoilSet, FusionKernel, validate_config  # noqa: F401
+from .fusion_kernel import (  # noqa: F401
+    BatchedFusionKernel, CoilSet, FusionKernel, shard_range, solve_sharded, validate_config,
+)
 from .multigrid_solve import (  # noqa: F401
     mg_residual, mg_smooth, multigrid_solve, multigrid_vcycle, prolongate_bilinear, residual_linf,
     restrict_full_weight, validate_sor_omega,

@@ -510,6 +510,52 @@ def _picard_run(k: _GridMixin, params, psi0: np.ndarray, bc: np.ndarray, ip: np.
     return out
 
 
+def shard_range(total: int, world: int, rank: int) -> tuple[int, int]:
+    """Contiguous slice [lo, hi) of `total` independent equilibria owned by `rank` (SURVEY.md 8e:
+    batched equilibria shard with no cross-GPU traffic; sizes differ by at most one)."""
+    if world < 1 or not (0 <= rank < world) or total < 0:
+        raise ValueError("bad shard arguments")
+    base, extra = divmod(total, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def solve_sharded(kernel, coil_currents, plasma_current=None, ped_p=None, ped_ff=None, *, group=None,
+                  gather: bool = True) -> dict[str, Any]:
+    """Solve a batch of independent equilibria sharded over the ranks of a torch.distributed group.
+
+    Every rank passes the FULL per-sample input arrays and solves only its `shard_range` slice with
+    ``kernel.solve`` (a ``BatchedFusionKernel``); no data-path collective runs during the solves.
+    With ``gather`` the per-equilibrium scalars (iterations, converged, residual, axis, X-point ...)
+    are all-gathered afterwards so every rank sees the summary of the whole batch; the flux maps stay
+    on the rank that computed them (``res["psi"]`` holds rows [lo, hi) only).
+    """
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    cc = np.asarray(coil_currents, dtype=np.float64)
+    total = cc.shape[0]
+    lo, hi = shard_range(total, world, rank)
+    pick = lambda a: None if a is None else np.asarray(a, dtype=np.float64)[lo:hi]
+    res = kernel.solve(cc[lo:hi], pick(plasma_current), pick(ped_p), pick(ped_ff)) if hi > lo else {}
+    res["shard"] = (lo, hi)
+    if gather and world > 1:
+        scalars = {k: v for k, v in res.items() if isinstance(v, np.ndarray) and v.ndim == 1}
+        parts: list = [None] * world
+        dist.all_gather_object(parts, ((lo, hi), scalars), group=group)
+        keys = sorted({k for _, sc in parts for k in sc})
+        merged = {}
+        for k in keys:
+            ref = next(sc[k] for _, sc in parts if k in sc)
+            out = np.zeros(total, dtype=ref.dtype)
+            for (a, b), sc in parts:
+                if b > a:
+                    out[a:b] = sc[k]
+            merged[k] = out
+        res["global"] = merged
+    return res
+
+
 class BatchedFusionKernel(_GridMixin):
     """B independent equilibria on one geometry (UQ / reconstruction / design sweeps).
 

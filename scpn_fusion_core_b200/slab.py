@@ -210,20 +210,24 @@ class SlabComm:
         dist = self.dist
         ops, recvs = [], []
         own0, own1 = L.h_top, L.h_top + (L.g1 - L.g0)
+        direct = not (self.backend == "gloo" and x.is_cuda)  # row blocks are contiguous views: no staging copies
+
+        def post(send_rows, recv_rows, peer):
+            send = x[send_rows] if direct else x[send_rows].cpu()
+            recv = x[recv_rows] if direct else self.torch.empty_like(send)
+            ops.append(dist.P2POp(dist.isend, send, peer, self.group))
+            ops.append(dist.P2POp(dist.irecv, recv, peer, self.group))
+            recvs.append((recv, recv_rows))
+
         if L.h_top:  # upper neighbour: send my first k owned rows, receive its last k owned rows
-            send = self._stage(x[own0:own0 + k].contiguous())
-            recv = self.torch.empty_like(send)
-            ops += [dist.P2POp(dist.isend, send, self.rank - 1, self.group), dist.P2POp(dist.irecv, recv, self.rank - 1, self.group)]
-            recvs.append((recv, slice(own0 - k, own0)))
+            post(slice(own0, own0 + k), slice(own0 - k, own0), self.rank - 1)
         if L.h_bot:
-            send = self._stage(x[own1 - k:own1].contiguous())
-            recv = self.torch.empty_like(send)
-            ops += [dist.P2POp(dist.isend, send, self.rank + 1, self.group), dist.P2POp(dist.irecv, recv, self.rank + 1, self.group)]
-            recvs.append((recv, slice(own1, own1 + k)))
+            post(slice(own1 - k, own1), slice(own1, own1 + k), self.rank + 1)
         for r in dist.batch_isend_irecv(ops):
             r.wait()
         for recv, sl in recvs:
-            x[sl].copy_(recv)
+            if not direct:
+                x[sl].copy_(recv)
             self.bytes_sent += recv.numel() * 8
             self.messages += 1
 

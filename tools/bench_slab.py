@@ -17,7 +17,7 @@ if world > 1:
     dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
 R = np.linspace(4.0, 8.0, n); Z = np.linspace(-4.0, 4.0, n)
 comm = SlabComm(rank, world)
-mgs = SlabMultigrid(n, n, 4.0, 8.0, -4.0, 4.0, comm, CudaSlabOps(local), halo=6, min_rows=64)
+mgs = SlabMultigrid(n, n, 4.0, 8.0, -4.0, 4.0, comm, CudaSlabOps(local), halo=6, min_rows=int(os.environ.get("SLAB_MIN_ROWS", "128")))
 g0, g1 = mgs.owned_rows()
 rr, zz = np.meshgrid(R, Z[g0:g1])
 src = -np.exp(-((rr - 6.0) ** 2 + zz ** 2) / 0.5)   # bench_gpu_gs_solver._problem source, psi_bc = 0
