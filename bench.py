@@ -36,7 +36,7 @@ sys.path.insert(0, ROOT)
 GRID = 129
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu --set full capture
 # (profiles/), per launch at the headline configuration; None until a capture of the current kernel exists.
-TRAFFIC_NCU = None
+TRAFFIC_NCU = 147.845e9  # profiles/r1_v5_summary.md: 24.4 GB read + 123.4 GB written per launch at B = 4096 (ncu --set full)
 ITER_COILS = [(3.5, 3.0, -1.0), (8.0, 3.0, 4.0), (9.5, 0.0, 6.0), (8.0, -3.0, 4.0), (3.5, -3.0, -1.0),
               (9.5, 3.0, 3.0), (2.1, 0.0, 0.0)]
 
@@ -128,24 +128,50 @@ def run_reference_arm(args) -> None:
 
 # ------------------------------------------------------------------------------------ GPU arm
 class ClockSampler(threading.Thread):
+    """SM clock + throttle reasons sampled DURING the timed region.  Uses NVML in-process (a query costs
+    microseconds); spawning nvidia-smi every 200 ms stalls the driver long enough to distort the
+    host-driven e2e leg.  Falls back to nvidia-smi only if NVML is unavailable."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
         self.index, self.samples, self.stop_flag = index, [], threading.Event()
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+        r = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") \
+            else n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        bits = [getattr(n, "nvmlClocksThrottleReasonHwSlowdown", 0x8), getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20), getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0x4)]
+        return [str(sm), str(mx)] + ["Active" if (r & b) else "Not Active" for b in bits]
 
     def run(self):
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
-                parts = [p.strip() for p in out.strip().split(",")]
-                if len(parts) >= 6:
-                    self.samples.append(parts)
+                if self.nvml is not None:
+                    self.samples.append(self._sample_nvml())
+                else:
+                    out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                    parts = [p.strip() for p in out.strip().split(",")]
+                    if len(parts) >= 6:
+                        self.samples.append(parts)
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.05 if self.nvml is not None else 0.5)
 
     def summary(self):
         if not self.samples:
@@ -155,7 +181,7 @@ class ClockSampler(threading.Thread):
         reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
         return {"sm_mhz": statistics.median(sm) if sm else None,
                 "sm_max_mhz": float(self.samples[0][1]) if self.samples[0][1].replace(".", "").isdigit() else None,
-                "reasons": reasons, "samples": len(self.samples)}
+                "reasons": reasons, "samples": len(self.samples), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def measured_peak_hbm():
