@@ -263,6 +263,94 @@ k_wall_gemm(const double *__restrict__ M, const double *__restrict__ J, int nz, 
     }
 }
 
+// Large-batch variant: CTA tile 128(b) x 64(w), K step 16, 8 warps laid out 4(b) x 2(w), each warp a
+// 32 x 32 sub-tile = 4 x 4 m8n8k4 accumulators (two shared loads per DMMA instead of three quarters
+// of one per DMMA... 8 LDS.64 feed 16 DMMA).  The K axis is walked as (interior row, 16-column
+// chunk) so a K tile never straddles a grid row: no integer division in the gather, and the
+// 16-column chunks of a row are contiguous in J and in M.  The next tile is fetched into registers
+// while the current one is multiplied (one barrier pair per K step, global latency hidden).
+constexpr int HB = 128, HW = 64, HK = 16;
+__global__ void __launch_bounds__(256, 2)
+k_wall_gemm_big(const double *__restrict__ M, const double *__restrict__ J, int nz, int nr, int batch, int nwall,
+                int nint, double dA, int tiles_per_split, double *__restrict__ out /*[split][B][Nw]*/) {
+  extern __shared__ double gsm[];  // two stages of { sX[HK][HB+4] ([k][b]), sM[HK][HW+4] ([k][w]) }
+  constexpr int LDX = HB + 4, LDM = HW + 4, STAGE = HK * (LDX + LDM);
+  const int b0 = blockIdx.x * HB, w0 = blockIdx.y * HW;
+  const int ncol = nr - 2;                      // interior columns per grid row
+  const int cpr = (ncol + HK - 1) / HK;         // 16-column chunks per row
+  const int ntiles = (nz - 2) * cpr;
+  const int t_beg = blockIdx.z * tiles_per_split, t_end = min(ntiles, t_beg + tiles_per_split);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wb = (warp >> 1) * 32, ww = (warp & 1) * 32;
+  const int gid = lane >> 2, tig = lane & 3;
+  const size_t n = (size_t)nz * nr;
+  // loader roles: X tile 128 b x 16 k -> thread (b = tid/2, 8 consecutive k); M tile 64 w x 16 k -> (w = tid/4, 4 k)
+  const int xb = tid >> 1, xk = (tid & 1) * 8;
+  const int mw = tid >> 2, mk = (tid & 3) * 4;
+  const bool xb_ok = b0 + xb < batch, mw_ok = w0 + mw < nwall;
+  const double *jrow = J + (size_t)min(b0 + xb, batch - 1) * n;
+  const double *mrow = M + (size_t)min(w0 + mw, nwall - 1) * nint;
+  double acc[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  double px[8], pm[4];
+  auto fetch = [&](int t) {
+    const int row = t / cpr, c0 = (t - row * cpr) * HK;  // once per K tile, not per element
+    const double *jp = jrow + (size_t)(row + 1) * nr + 1 + c0 + xk;
+    const double *mp = mrow + (size_t)row * ncol + c0 + mk;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) px[q] = (xb_ok && c0 + xk + q < ncol) ? jp[q] * dA : 0.0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) pm[q] = (mw_ok && c0 + mk + q < ncol) ? mp[q] : 0.0;
+  };
+  auto stash = [&](int stage) {
+    double *sX = gsm + stage * STAGE, *sM = sX + HK * LDX;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) sX[(xk + q) * LDX + xb] = px[q];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) sM[(mk + q) * LDM + mw] = pm[q];
+  };
+  if (t_beg < t_end) {
+    fetch(t_beg);
+    stash(0);
+  }
+  __syncthreads();
+  int cur = 0;
+  for (int t = t_beg; t < t_end; ++t) {
+    if (t + 1 < t_end) fetch(t + 1);  // global loads of the next tile fly during the multiply
+    const double *sX = gsm + cur * STAGE, *sM = sX + HK * LDX;
+#pragma unroll
+    for (int ks = 0; ks < HK; ks += 4) {
+      double a[4], bfr[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = sX[(ks + tig) * LDX + wb + i * 8 + gid];    // A[row=gid][k=tig]
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bfr[j] = sM[(ks + tig) * LDM + ww + j * 8 + gid];  // B[k=tig][col=gid]
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], bfr[j]);
+    }
+    if (t + 1 < t_end) stash(1 - cur);  // the other stage was last read before the previous barrier
+    __syncthreads();
+    cur ^= 1;
+  }
+  double *o = out + (size_t)blockIdx.z * batch * nwall;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int b = b0 + wb + i * 8 + gid;
+      const int w = w0 + ww + j * 8 + 2 * tig;
+      if (b < batch) {
+        if (w < nwall) o[(size_t)b * nwall + w] = acc[i][j][0];
+        if (w + 1 < nwall) o[(size_t)b * nwall + w + 1] = acc[i][j][1];
+      }
+    }
+}
+
 __global__ void k_splitk_reduce(const double *__restrict__ part, int splits, size_t total,
                                 double *__restrict__ out) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -374,6 +462,32 @@ int gsb_wall_flux(gsb_ctx *ctx, const double *m_dev, const double *jphi_dev, dou
   GSB_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = (cudaStream_t)stream;
   const int nw = ctx->n_wall, ni = ctx->n_int;
+  if (batch >= HB) {  // large batches: 128 x 64 tiles, register double buffering
+    const int cpr = (ctx->nr - 2 + HK - 1) / HK, ntiles = (ctx->nz - 2) * cpr;
+    const int ctas = ((batch + HB - 1) / HB) * ((nw + HW - 1) / HW);
+    int splits = 1;
+    while (ctas * splits < 2 * ctx->num_sms && splits < 16 && ntiles / (splits * 2) >= 64) splits *= 2;
+    const int tps = (ntiles + splits - 1) / splits;
+    splits = (ntiles + tps - 1) / tps;
+    double *part = wall_dev;
+    if (splits > 1) GSB_CUDA(cudaMallocAsync(&part, (size_t)splits * batch * nw * sizeof(double), st));
+    constexpr int kBigSmem = 2 * HK * (HB + 4 + HW + 4) * (int)sizeof(double);
+    static bool attr_set = false;
+    if (!attr_set) {
+      GSB_CUDA(cudaFuncSetAttribute(k_wall_gemm_big, cudaFuncAttributeMaxDynamicSharedMemorySize, kBigSmem));
+      attr_set = true;
+    }
+    k_wall_gemm_big<<<dim3((batch + HB - 1) / HB, (nw + HW - 1) / HW, splits), 256, kBigSmem, st>>>(
+        m_dev, jphi_dev, ctx->nz, ctx->nr, batch, nw, ni, dA, tps, part);
+    GSB_LAUNCH_CHECK();
+    if (splits > 1) {
+      const size_t total = (size_t)batch * nw;
+      k_splitk_reduce<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(part, splits, total, wall_dev);
+      GSB_LAUNCH_CHECK();
+      GSB_CUDA(cudaFreeAsync(part, st));
+    }
+    return GSB_OK;
+  }
   const int tiles = ((batch + GB - 1) / GB) * ((nw + GW - 1) / GW);
   int splits = 1;
   while (tiles * splits < 148 * 2 && splits < 32 && ni / (splits * 2) >= 512) splits *= 2;

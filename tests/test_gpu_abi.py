@@ -60,13 +60,13 @@ def test_wall_response_matrix_and_flux(monkeypatch):
     R = np.linspace(1.0, 3.0, nr)
     Z = np.linspace(-1.5, 1.5, nz)
     dr, dz = float(R[1] - R[0]), float(Z[1] - Z[0])
-    ctx = D.get_context(nz, nr, R, Z, dr, dz, 80, 0)
+    ctx = D.get_context(nz, nr, R, Z, dr, dz, 300, 0)
     M_ref, b_idx, s_idx = G.wall_response_matrix(R, Z)
     m = D.empty(M_ref.shape, 0)
     _lib.check(ctx.lib.gsb_wall_matrix(ctx.handle, G.MU0_SI, D.ptr(m), D.stream_ptr()))
     np.testing.assert_allclose(m.cpu().numpy(), M_ref, rtol=2e-14, atol=0)
     rng = np.random.default_rng(1)
-    for B in (1, 7, 80):
+    for B in (1, 7, 80, 128, 300):  # >= 128 takes the large-batch tile kernel
         J = rng.normal(size=(B, nz, nr))
         dA = dr * dz
         Jd = D.to_device(J, 0)
