@@ -589,6 +589,7 @@ struct PicardResArgs {
   double *ws_src;           // [grid][2*nz*hw]     right-hand side, colour-split
   const double *seedJ, *cf, *mr, *rrow;
   const int *rowmask;
+  int *queue;               // work queue: next unclaimed equilibrium = gridDim.x + atomicAdd(queue, 1)
   double seed_sum_drdz;
   int batch, max_iter, seed, saddle, need_gs;
   double tol, gs_tol, alpha, oma, omega;
@@ -752,7 +753,9 @@ k_picard_resident(const __grid_constant__ RPlan plan, const __grid_constant__ Pi
     }                                                                          \
   }
 
-  for (int b = blockIdx.x; b < a.batch; b += gridDim.x) {
+  // equilibria need different numbers of Picard iterations: CTAs claim the next one from a queue
+  // instead of striding, so no SM idles while another still has several solves lined up
+  for (int b = blockIdx.x; b < a.batch;) {
     const double *bc = a.bc + (size_t)b * n;
     const double ipb = a.ip[b];
     double pp[4], pf[4];
@@ -1187,7 +1190,10 @@ k_picard_resident(const __grid_constant__ RPlan plan, const __grid_constant__ Pi
       const int newcur = nxt;
       if (improved) best = newcur;
       cur = newcur;
-      nxt = (cur == best) ? (cur + 1) % 3 : 3 - cur - best;
+      // next slot: the lowest one that holds neither the current nor the best iterate (while every
+      // iteration improves, best == cur and the solve ping-pongs between two slots only: the third
+      // stays out of the L2 working set)
+      nxt = (cur == best) ? (cur == 0 ? 1 : 0) : 3 - cur - best;
       if (code != 0) {
         status = code;
         break;
@@ -1225,6 +1231,10 @@ k_picard_resident(const __grid_constant__ RPlan plan, const __grid_constant__ Pi
         o[15] = 0.0;
       }
     }
+    __syncthreads();
+    if (threadIdx.x == 0) res_pool[bslot] = (double)(gridDim.x + atomicAdd(a.queue, 1));
+    __syncthreads();
+    b = (int)res_pool[bslot];
     __syncthreads();
   }
 #undef GSB_SLOT_LOOP_BEGIN
@@ -1414,6 +1424,8 @@ static int picard_resident_launch(gsb_ctx *ctx, const gsb_picard_params *p, doub
   a.mr = w->mr;
   a.rrow = ctx->r_dev;
   a.rowmask = w->rowmask;
+  a.queue = ctx->counter + 1;
+  GSB_CUDA(cudaMemsetAsync(a.queue, 0, sizeof(int), st));
   {
     volatile double ssum = w->seed_sum * ctx->dr;
     volatile double ssum2 = ssum * ctx->dz;
