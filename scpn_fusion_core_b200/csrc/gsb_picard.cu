@@ -589,7 +589,6 @@ struct PicardResArgs {
   double *ws_src;           // [grid][2*nz*hw]     right-hand side, colour-split
   const double *seedJ, *cf, *mr, *rrow;
   const int *rowmask;
-  int *queue;               // work queue: next unclaimed equilibrium = gridDim.x + atomicAdd(queue, 1)
   double seed_sum_drdz;
   int batch, max_iter, seed, saddle, need_gs;
   double tol, gs_tol, alpha, oma, omega;
@@ -753,9 +752,8 @@ k_picard_resident(const __grid_constant__ RPlan plan, const __grid_constant__ Pi
     }                                                                          \
   }
 
-  // equilibria need different numbers of Picard iterations: CTAs claim the next one from a queue
-  // instead of striding, so no SM idles while another still has several solves lined up
-  for (int b = blockIdx.x; b < a.batch;) {
+  // static striding (a dynamic work queue was measured 10-25 % SLOWER: see profiles/r1_v5_summary.md)
+  for (int b = blockIdx.x; b < a.batch; b += gridDim.x) {
     const double *bc = a.bc + (size_t)b * n;
     const double ipb = a.ip[b];
     double pp[4], pf[4];
@@ -1232,10 +1230,6 @@ k_picard_resident(const __grid_constant__ RPlan plan, const __grid_constant__ Pi
       }
     }
     __syncthreads();
-    if (threadIdx.x == 0) res_pool[bslot] = (double)(gridDim.x + atomicAdd(a.queue, 1));
-    __syncthreads();
-    b = (int)res_pool[bslot];
-    __syncthreads();
   }
 #undef GSB_SLOT_LOOP_BEGIN
 #undef GSB_SLOT_LOOP_END
@@ -1424,8 +1418,6 @@ static int picard_resident_launch(gsb_ctx *ctx, const gsb_picard_params *p, doub
   a.mr = w->mr;
   a.rrow = ctx->r_dev;
   a.rowmask = w->rowmask;
-  a.queue = ctx->counter + 1;
-  GSB_CUDA(cudaMemsetAsync(a.queue, 0, sizeof(int), st));
   {
     volatile double ssum = w->seed_sum * ctx->dr;
     volatile double ssum2 = ssum * ctx->dz;
