@@ -258,7 +258,9 @@ int gsb_create(gsb_ctx **out, int nz, int nr, const double *r_row, const double 
   };
   A((void **)&ctx->r_dev, nr * sizeof(double));
   A((void **)&ctx->z_dev, nz * sizeof(double));
-  A((void **)&ctx->red, (size_t)batch_cap * kRedStride * sizeof(double));
+  // reduction scratch: at least 8192 doubles in total so a single large grid can use thousands of partial blocks
+  ctx->red_stride = std::max(kRedStride, (8192 + batch_cap - 1) / batch_cap);
+  A((void **)&ctx->red, (size_t)batch_cap * ctx->red_stride * sizeof(double));
   A((void **)&ctx->active, (size_t)batch_cap * sizeof(int));
   A((void **)&ctx->counter, 4 * sizeof(int));
   A((void **)&ctx->mg_bc, (size_t)batch_cap * ring_size(nz, nr) * sizeof(double));

@@ -303,7 +303,8 @@ struct gsb_ctx {
   double *z_dev = nullptr;  // [nz]
   double *r_dev = nullptr;  // [nr]
   // scratch for reductions / mg_solve
-  double *red = nullptr;    // [batch_cap][kRedStride]
+  double *red = nullptr;    // [batch_cap][red_stride] reduction partials
+  int red_stride = 0;       // doubles per equilibrium: >= kRedStride, larger for small batch_cap (big grids)
   int *active = nullptr;    // [batch_cap]
   int *counter = nullptr;   // device counter
   int *h_counter = nullptr; // pinned host mirror

@@ -148,7 +148,7 @@ k_residual(LevelGeom g, const double *__restrict__ psi, const double *__restrict
 __global__ void __launch_bounds__(256)
 k_residual_norm_partials(LevelGeom g, const double *__restrict__ psi, size_t pstride,
                          const double *__restrict__ src, size_t sstride, double *__restrict__ red,
-                         const int *__restrict__ active) {
+                         int red_stride, const int *__restrict__ active) {
   __shared__ double sh[32];
   const int b = blockIdx.y, P = gridDim.x, p = blockIdx.x;
   if (active && !active[b]) return;
@@ -157,25 +157,26 @@ k_residual_norm_partials(LevelGeom g, const double *__restrict__ psi, size_t pst
   double mx = 0.0, sq = 0.0;
   const double *base = psi + (size_t)b * pstride;
   const double *sb = src + (size_t)b * sstride;
-  for (int idx = threadIdx.x; idx < (r1 - r0) * cols; idx += blockDim.x) {
-    const int iz = 1 + r0 + idx / cols, ir = 1 + idx % cols;
-    const double *q = base + (size_t)iz * g.nr + ir;
-    double r = dsub(gs_apply(g, ir, q[0], q[1], q[-1], q[-g.nr], q[g.nr]), sb[(size_t)iz * g.nr + ir]);
-    // NaN must survive the max (np.max propagates NaN)
-    const double a = fabs(r);
-    mx = (isnan(a) || isnan(mx)) ? NAN : fmax(mx, a);
-    sq += r * r;
-  }
+  // rows of the block's band one at a time, threads across the columns (no integer division per point)
+  for (int iz = 1 + r0; iz < 1 + r1; ++iz)
+    for (int ir = 1 + threadIdx.x; ir <= cols; ir += blockDim.x) {
+      const double *q = base + (size_t)iz * g.nr + ir;
+      double r = dsub(gs_apply(g, ir, q[0], q[1], q[-1], q[-g.nr], q[g.nr]), sb[(size_t)iz * g.nr + ir]);
+      // NaN must survive the max (np.max propagates NaN)
+      const double a = fabs(r);
+      mx = (isnan(a) || isnan(mx)) ? NAN : fmax(mx, a);
+      sq += r * r;
+    }
   const bool anynan = __syncthreads_or(isnan(mx));
   double m = block_max(isnan(mx) ? 0.0 : mx, sh);
   double s = block_sum(sq, sh);
   if (threadIdx.x == 0) {
-    red[(size_t)b * kRedStride + 2 * p] = anynan ? NAN : m;
-    red[(size_t)b * kRedStride + 2 * p + 1] = s;
+    red[(size_t)b * red_stride + 2 * p] = anynan ? NAN : m;
+    red[(size_t)b * red_stride + 2 * p + 1] = s;
   }
 }
 
-__global__ void k_residual_norm_final(const double *__restrict__ red, int P, double n_int,
+__global__ void k_residual_norm_final(const double *__restrict__ red, int red_stride, int P, double n_int,
                                       double *__restrict__ linf, double *__restrict__ rms, int batch,
                                       const int *__restrict__ active) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -184,20 +185,21 @@ __global__ void k_residual_norm_final(const double *__restrict__ red, int P, dou
   double m = 0.0, s = 0.0;
   bool nan = false;
   for (int p = 0; p < P; ++p) {
-    const double v = red[(size_t)b * kRedStride + 2 * p];
+    const double v = red[(size_t)b * red_stride + 2 * p];
     if (isnan(v)) nan = true;
     m = fmax(m, v);
-    s += red[(size_t)b * kRedStride + 2 * p + 1];
+    s += red[(size_t)b * red_stride + 2 * p + 1];
   }
   if (linf) linf[b] = nan ? NAN : m;
   if (rms) rms[b] = (n_int > 0) ? sqrt(s / n_int) : 0.0;
 }
 
-static int norm_partials(const LevelGeom &g) {
+static int norm_partials(const LevelGeom &g, int red_stride) {
   const long long pts = (long long)(g.nz - 2) * (g.nr - 2);
   int P = (int)((pts + 4095) / 4096);
   if (P < 1) P = 1;
-  if (P > kRedStride / 2) P = kRedStride / 2;
+  if (P > red_stride / 2) P = red_stride / 2;
+  if (P > 2048) P = 2048;
   if (P > g.nz - 2) P = g.nz - 2 > 0 ? g.nz - 2 : 1;
   return P;
 }
@@ -210,11 +212,11 @@ int residual_norms_launch(gsb_ctx *ctx, const LevelGeom &g, const double *psi, s
     if (rms) GSB_CUDA(cudaMemsetAsync(rms, 0, batch * sizeof(double), st));
     return GSB_OK;
   }
-  const int P = norm_partials(g);
-  k_residual_norm_partials<<<dim3(P, batch), 256, 0, st>>>(g, psi, pstride, src, sstride, ctx->red, active);
+  const int P = norm_partials(g, ctx->red_stride);
+  k_residual_norm_partials<<<dim3(P, batch), 256, 0, st>>>(g, psi, pstride, src, sstride, ctx->red, ctx->red_stride, active);
   GSB_LAUNCH_CHECK();
   k_residual_norm_final<<<(batch + 127) / 128, 128, 0, st>>>(
-      ctx->red, P, (double)(g.nz - 2) * (double)(g.nr - 2), linf, rms, batch, active);
+      ctx->red, ctx->red_stride, P, (double)(g.nz - 2) * (double)(g.nr - 2), linf, rms, batch, active);
   GSB_LAUNCH_CHECK();
   return GSB_OK;
 }
