@@ -246,6 +246,27 @@ int gsb_slab_prolong_add(gsb_ctx *fine, const double *ec_dev, int nzc_loc, int n
 int gsb_slab_residual_linf(gsb_ctx *ctx, const double *x_dev, const double *src_dev, int row0, int row1,
                            double *out_dev, void *stream);
 
+/* Halo exchange over NVLink peer memory (CUDA IPC; no NCCL launch).  Every rank owns two inboxes
+ * and a block of four int64 flags {ready_from_up, ready_from_dn, consumed_by_up, consumed_by_dn} that
+ * its neighbours can address.  gsb_halo_push stores `n` doubles of boundary rows straight into the
+ * neighbours' inboxes and raises their ready flags; gsb_halo_recv waits for its own ready flags,
+ * copies inbox -> halo rows and releases the senders.  `epochs` = four zero-initialised int64 of LOCAL
+ * device scratch (exchange counters, kept on the device so a captured CUDA graph can be replayed);
+ * both sides must issue the same sequence of exchanges; NULL row pointers = no neighbour on that side. */
+int gsb_enable_peer_access(int device, int peer_device);
+/* CUDA IPC plumbing for the inboxes/flags: a zero-filled cudaMalloc block + its 64-byte handle; the
+ * neighbours map it with gsb_ipc_open. */
+int gsb_ipc_alloc(int device, long long bytes, void **ptr_out, unsigned char *handle_out64);
+int gsb_ipc_open(int device, const unsigned char *handle64, void **ptr_out);
+int gsb_ipc_close(void *ptr);
+int gsb_ipc_free(void *ptr);
+int gsb_halo_push(const double *rows_up, const double *rows_dn, long long n, double *up_inbox_dn, double *dn_inbox_up,
+                  long long *flags_local, long long *flags_up, long long *flags_dn, int *counters, long long *epochs,
+                  void *stream);
+int gsb_halo_recv(double *halo_up, double *halo_dn, long long n, const double *inbox_up, const double *inbox_dn,
+                  long long *flags_local, long long *flags_up, long long *flags_dn, int *counters, long long *epochs,
+                  void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -71,6 +71,15 @@ SIGNATURES = {
     "gsb_picard_solve": (c_int, [c_void_p, POINTER(gsb_picard_params), c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "gsb_picard_last_launched_iterations": (c_int, [c_void_p]),
+    "gsb_enable_peer_access": (c_int, [c_int, c_int]),
+    "gsb_ipc_alloc": (c_int, [c_int, c_longlong, POINTER(c_void_p), c_char_p]),
+    "gsb_ipc_open": (c_int, [c_int, c_char_p, POINTER(c_void_p)]),
+    "gsb_ipc_close": (c_int, [c_void_p]),
+    "gsb_ipc_free": (c_int, [c_void_p]),
+    "gsb_halo_push": (c_int, [c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                              c_void_p, c_void_p]),
+    "gsb_halo_recv": (c_int, [c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                              c_void_p, c_void_p]),
     "gsb_slab_single_tile": (c_int, [c_void_p, c_int]),
     "gsb_slab_smooth": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_int, c_int, c_void_p]),
     "gsb_slab_residual_restrict": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,

@@ -176,22 +176,31 @@ k_residual_norm_partials(LevelGeom g, const double *__restrict__ psi, size_t pst
   }
 }
 
-__global__ void k_residual_norm_final(const double *__restrict__ red, int red_stride, int P, double n_int,
-                                      double *__restrict__ linf, double *__restrict__ rms, int batch,
-                                      const int *__restrict__ active) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128)
+k_residual_norm_final(const double *__restrict__ red, int red_stride, int P, double n_int,
+                      double *__restrict__ linf, double *__restrict__ rms, int batch,
+                      const int *__restrict__ active) {
+  // one CTA per equilibrium: fixed-tree reduction of the P partial (max, sum) pairs
+  __shared__ double sh[32];
+  const int b = blockIdx.x;
   if (b >= batch) return;
   if (active && !active[b]) return;
   double m = 0.0, s = 0.0;
-  bool nan = false;
-  for (int p = 0; p < P; ++p) {
+  int nan = 0;
+  for (int p = threadIdx.x; p < P; p += blockDim.x) {
     const double v = red[(size_t)b * red_stride + 2 * p];
-    if (isnan(v)) nan = true;
+    if (isnan(v)) nan = 1;
     m = fmax(m, v);
     s += red[(size_t)b * red_stride + 2 * p + 1];
   }
-  if (linf) linf[b] = nan ? NAN : m;
-  if (rms) rms[b] = (n_int > 0) ? sqrt(s / n_int) : 0.0;
+  nan = __syncthreads_or(nan);
+  m = block_max(m, sh);
+  __syncthreads();
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) {
+    if (linf) linf[b] = nan ? NAN : m;
+    if (rms) rms[b] = (n_int > 0) ? sqrt(s / n_int) : 0.0;
+  }
 }
 
 static int norm_partials(const LevelGeom &g, int red_stride) {
@@ -215,7 +224,7 @@ int residual_norms_launch(gsb_ctx *ctx, const LevelGeom &g, const double *psi, s
   const int P = norm_partials(g, ctx->red_stride);
   k_residual_norm_partials<<<dim3(P, batch), 256, 0, st>>>(g, psi, pstride, src, sstride, ctx->red, ctx->red_stride, active);
   GSB_LAUNCH_CHECK();
-  k_residual_norm_final<<<(batch + 127) / 128, 128, 0, st>>>(
+  k_residual_norm_final<<<batch, 128, 0, st>>>(
       ctx->red, ctx->red_stride, P, (double)(g.nz - 2) * (double)(g.nr - 2), linf, rms, batch, active);
   GSB_LAUNCH_CHECK();
   return GSB_OK;

@@ -10,6 +10,8 @@
 //     the local fine and coarse indices (fine local row = 2 * coarse local row + roff).
 #include "gsb_internal.cuh"
 
+#include <cstring>
+
 namespace gsb {
 
 // coarse local rows [ci0, ci1), all coarse columns; column walls get 0 (multigrid_solve.py:303-306)
@@ -87,6 +89,68 @@ k_slab_residual_linf(LevelGeom g, const double *__restrict__ psi, const double *
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Halo exchange over NVLink peer memory (no NCCL launch): every rank exposes two inboxes and a
+// flag block through CUDA IPC.  push: wait until the neighbour has consumed the previous message,
+// store my boundary rows straight into the neighbour's inbox (posted remote writes), fence, then
+// raise the neighbour's ready flag.  recv: spin on my own (local) ready flag, copy inbox -> halo
+// rows, then tell the sender it may overwrite the inbox.  Epochs count exchanges; both sides issue
+// the same sequence, so the flags are monotone.  Multi-CTA: the last CTA to finish (atomic counter)
+// publishes the flag.
+// flags (int64, in the OWNER's memory): [0] ready_from_up  [1] ready_from_dn   (written by neighbours)
+//                                        [2] consumed_by_up [3] consumed_by_dn  (written by neighbours)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ long long ld_sys(const long long *p) {
+  long long v;
+  asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_sys(long long *p, long long v) {
+  asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+struct HaloDir {
+  const double *src;       // push: my boundary rows            recv: my inbox
+  double *dst;             // push: the neighbour's inbox       recv: my halo rows
+  const long long *wait;   // flag to wait on (local memory)
+  long long *signal;       // flag to raise afterwards (push: neighbour's ready; recv: neighbour's consumed)
+  long long *epoch;        // local device counter of completed exchanges in this direction (graph-replay safe:
+                           // the epoch is read on the device, not baked into the launch)
+  int wait_lag;            // wait until *wait >= epoch - wait_lag  (push: 1 = previous message consumed; recv: 0)
+  int *counter;            // local CTA-arrival counter of this direction
+};
+struct HaloArgs {
+  HaloDir d[2];
+  long long n;      // doubles per direction
+};
+
+__global__ void __launch_bounds__(512) k_halo_copy(const HaloArgs a) {
+  const HaloDir &D = a.d[blockIdx.y];
+  if (!D.src) return;
+  __shared__ long long s_epoch;
+  if (threadIdx.x == 0) {
+    const long long e = ld_sys(D.epoch) + 1;  // this exchange's number; bumped by the last CTA below
+    s_epoch = e;
+    while (ld_sys(D.wait) < e - D.wait_lag) __nanosleep(64);
+  }
+  __syncthreads();
+  const long long epoch = s_epoch;
+  const long long per = (a.n + gridDim.x - 1) / gridDim.x;
+  const long long i0 = per * blockIdx.x, i1 = min(a.n, i0 + per);
+  for (long long i = i0 + threadIdx.x; i < i1; i += blockDim.x) D.dst[i] = __ldcv(D.src + i);
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int arrived = atomicAdd(D.counter, 1);
+    if (arrived == (int)gridDim.x - 1) {  // last CTA of this direction: every CTA has read the epoch by now
+      *D.counter = 0;
+      *D.epoch = epoch;
+      __threadfence_system();
+      st_sys(D.signal, epoch);
+    }
+  }
+}
+
 static int slab_plan(gsb_ctx *ctx) {
   // a slab context has exactly one level: the local array itself
   return ensure_plan(ctx, 1 << 30);
@@ -97,6 +161,107 @@ static int slab_plan(gsb_ctx *ctx) {
 using namespace gsb;
 
 extern "C" {
+
+// Let kernels running on `device` dereference memory that lives on `peer_device` (needed before IPC-opened
+// neighbour buffers can be used by gsb_halo_push / gsb_halo_recv).  Returns GSB_OK if access is (already) enabled.
+int gsb_enable_peer_access(int device, int peer_device) {
+  if (device == peer_device) return GSB_OK;
+  int can = 0;
+  GSB_CUDA(cudaDeviceCanAccessPeer(&can, device, peer_device));
+  GSB_REQUIRE(can, "gsb_enable_peer_access: the two devices have no peer-to-peer path");
+  GSB_CUDA(cudaSetDevice(device));
+  cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) {
+    cudaGetLastError();
+    e = cudaSuccess;
+  }
+  GSB_CUDA(e);
+  return GSB_OK;
+}
+
+// One cudaMalloc'ed, zero-filled block that other processes can map (CUDA IPC): returns the local pointer
+// and the 64-byte cudaIpcMemHandle_t to hand to the neighbours.
+int gsb_ipc_alloc(int device, long long bytes, void **ptr_out, unsigned char *handle_out64) {
+  GSB_REQUIRE(ptr_out && handle_out64 && bytes > 0, "gsb_ipc_alloc: bad argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  GSB_CUDA(cudaSetDevice(device));
+  void *p = nullptr;
+  GSB_CUDA(cudaMalloc(&p, (size_t)bytes));
+  GSB_CUDA(cudaMemset(p, 0, (size_t)bytes));
+  GSB_CUDA(cudaDeviceSynchronize());
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    GSB_CUDA(e);
+  }
+  memcpy(handle_out64, &h, 64);
+  *ptr_out = p;
+  return GSB_OK;
+}
+// Map a neighbour's block into this process with `device` current (peer access is enabled lazily by the driver).
+int gsb_ipc_open(int device, const unsigned char *handle64, void **ptr_out) {
+  GSB_REQUIRE(ptr_out && handle64, "gsb_ipc_open: bad argument");
+  GSB_CUDA(cudaSetDevice(device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  GSB_CUDA(cudaIpcOpenMemHandle(ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+  return GSB_OK;
+}
+int gsb_ipc_close(void *ptr) {
+  if (ptr) GSB_CUDA(cudaIpcCloseMemHandle(ptr));
+  return GSB_OK;
+}
+int gsb_ipc_free(void *ptr) {
+  if (ptr) GSB_CUDA(cudaFree(ptr));
+  return GSB_OK;
+}
+
+// Push `n` doubles per direction into the neighbours' inboxes (NULL row pointer = no neighbour on that
+// side).  flags_local: this rank's flag block; flags_up/flags_dn: the neighbours' flag blocks and
+// inbox_*: their inboxes (peer pointers opened through CUDA IPC); counters: 4 ints and epochs: 4 int64 of local
+// scratch (zeroed once): {push up, push dn, recv up, recv dn}.  The exchange number lives on the device, so a
+// captured CUDA graph of a V-cycle can be replayed.
+int gsb_halo_push(const double *rows_up, const double *rows_dn, long long n, double *up_inbox_dn, double *dn_inbox_up,
+                  long long *flags_local, long long *flags_up, long long *flags_dn, int *counters, long long *epochs,
+                  void *stream) {
+  GSB_REQUIRE(flags_local && counters && epochs && n > 0, "gsb_halo_push: bad argument");
+  HaloArgs a{};
+  a.n = n;
+  if (rows_up) {
+    GSB_REQUIRE(up_inbox_dn && flags_up, "gsb_halo_push: upper neighbour buffers missing");
+    a.d[0] = HaloDir{rows_up, up_inbox_dn, flags_local + 2, flags_up + 1, epochs + 0, 1, counters + 0};
+  }
+  if (rows_dn) {
+    GSB_REQUIRE(dn_inbox_up && flags_dn, "gsb_halo_push: lower neighbour buffers missing");
+    a.d[1] = HaloDir{rows_dn, dn_inbox_up, flags_local + 3, flags_dn + 0, epochs + 1, 1, counters + 1};
+  }
+  const int nblk = (int)std::min<long long>(16, (n + 8191) / 8192);
+  k_halo_copy<<<dim3(nblk, 2), 512, 0, (cudaStream_t)stream>>>(a);
+  GSB_LAUNCH_CHECK();
+  return GSB_OK;
+}
+
+// Wait for the neighbours' pushes of `epoch`, copy my inboxes into my halo rows, release the inboxes.
+int gsb_halo_recv(double *halo_up, double *halo_dn, long long n, const double *inbox_up, const double *inbox_dn,
+                  long long *flags_local, long long *flags_up, long long *flags_dn, int *counters, long long *epochs,
+                  void *stream) {
+  GSB_REQUIRE(flags_local && counters && epochs && n > 0, "gsb_halo_recv: bad argument");
+  HaloArgs a{};
+  a.n = n;
+  if (halo_up) {
+    GSB_REQUIRE(inbox_up && flags_up, "gsb_halo_recv: upper neighbour buffers missing");
+    a.d[0] = HaloDir{inbox_up, halo_up, flags_local + 0, flags_up + 3, epochs + 2, 0, counters + 2};
+  }
+  if (halo_dn) {
+    GSB_REQUIRE(inbox_dn && flags_dn, "gsb_halo_recv: lower neighbour buffers missing");
+    a.d[1] = HaloDir{inbox_dn, halo_dn, flags_local + 1, flags_dn + 2, epochs + 3, 0, counters + 3};
+  }
+  const int nblk = (int)std::min<long long>(16, (n + 8191) / 8192);
+  k_halo_copy<<<dim3(nblk, 2), 512, 0, (cudaStream_t)stream>>>(a);
+  GSB_LAUNCH_CHECK();
+  return GSB_OK;
+}
 
 int gsb_slab_single_tile(gsb_ctx *ctx, int sweeps) {
   if (!ctx || sweeps < 1 || sweeps > 3) return 0;

@@ -206,7 +206,9 @@ void sweep_fused_plan(int nz, int nr, int batch, int nst, int num_sms, int *stri
   const long long warps = (long long)*n_strips * batch;
   const long long want = 24LL * num_sms;
   int bands = 1;
-  if (warps < want) bands = (int)std::min<long long>((want + warps - 1) / warps, std::max(1, nz / 96));
+  // a warp marches down its band row by row (~0.3 us per row step): short bands keep small levels from
+  // being latency bound; 32 rows is the floor (the 2*nst halo rows are recomputed per band)
+  if (warps < want) bands = (int)std::min<long long>((want + warps - 1) / warps, std::max(1, nz / 32));
   const int br = (nz + bands - 1) / bands;
   *band_rows = br;
   *n_bands = (nz + br - 1) / br;

@@ -58,7 +58,7 @@ class SlabLevel:
 
 
 def plan_slab_levels(nz: int, nr: int, r_min: float, r_max: float, z_min: float, z_max: float, world: int,
-                     rank: int, *, halo: int = 6, min_rows: int = 32, min_grid: int = 5) -> tuple[list[SlabLevel], dict]:
+                     rank: int, *, halo: int = 12, min_rows: int = 32, min_grid: int = 5) -> tuple[list[SlabLevel], dict]:
     """Row partition of every distributed level plus the geometry of the first gathered level.
 
     Needs nz = 2^p + 1 rows with (nz-1) divisible by world; a level stays distributed while it has at
@@ -132,8 +132,9 @@ class CudaSlabOps:
             self._ctx[key] = self.D.Context(L.rows_loc, L.nr, L.r_row, None, L.dr, L.dz, 1, self.device)
         return self._ctx[key]
 
-    def smooth(self, L: SlabLevel, x, f, omega: float, sweeps: int):
-        """``sweeps`` RB-SOR sweeps of the local array; returns the tensor holding the result."""
+    def smooth(self, L: SlabLevel, x, f, omega: float, sweeps: int, out=None):
+        """``sweeps`` RB-SOR sweeps of the local array; returns the tensor holding the result
+        (``out`` if given and usable for the last pass, so a V-cycle can end in the buffer it started in)."""
         D = self.D
         ctx = self._context(L)
         st = D.stream_ptr()
@@ -145,10 +146,15 @@ class CudaSlabOps:
                 dst = cur
             else:  # out of place: write into a cached buffer of this shape that is not the input
                 pool = self._alt.setdefault((L.rows_loc, L.nr), [])
-                dst = next((b for b in pool if b.data_ptr() != cur.data_ptr()), None)
-                if dst is None:
-                    dst = D.empty(tuple(x.shape), self.device)
-                    pool.append(dst)
+                last = left <= 3
+                if last and out is not None and out.data_ptr() != cur.data_ptr():
+                    dst = out
+                else:
+                    dst = next((b for b in pool if b.data_ptr() != cur.data_ptr()
+                                and (out is None or b.data_ptr() != out.data_ptr())), None)
+                    if dst is None:
+                        dst = D.empty(tuple(x.shape), self.device)
+                        pool.append(dst)
             _lib.check(ctx.lib.gsb_slab_smooth(ctx.handle, D.ptr(cur), D.ptr(dst), D.ptr(f), omega, s, L.row0, st),
                        "gsb_slab_smooth")
             cur = dst
@@ -199,6 +205,70 @@ class SlabComm:
         self.bytes_sent = 0
         self.messages = 0
 
+    def enable_peer_halo(self, device: int, max_doubles: int) -> bool:
+        """Exchange halos over NVLink peer memory with libgsb200's own push/recv kernels instead of NCCL
+        point-to-point launches (one process per GPU, buffers shared through CUDA IPC).  Collective:
+        every rank of the group must call it.  Returns False (and keeps NCCL) if IPC is unavailable."""
+        self.peer = None
+        if self.world == 1:
+            return False
+        import ctypes as C
+        torch, dist = self.torch, self.dist
+        lib = _lib.load()
+        dev = torch.device(f"cuda:{device}")
+        # one IPC block per rank: [4 int64 flags | pad to 256 B | inbox_up | inbox_dn]
+        inbox_bytes = ((max_doubles * 8 + 255) // 256) * 256
+        total = 256 + 2 * inbox_bytes
+        base = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        ok = 1 if lib.gsb_ipc_alloc(device, total, C.byref(base), handle) == 0 else 0
+        gathered: list = [None] * self.world
+        dist.all_gather_object(gathered, (ok, bytes(handle.raw), device), group=self.group)
+        if not all(g[0] for g in gathered):
+            if ok:
+                lib.gsb_ipc_free(base)
+            return False
+        peers = {}
+        for name, r in (("up", self.rank - 1), ("dn", self.rank + 1)):
+            if 0 <= r < self.world:
+                p = C.c_void_p()
+                if lib.gsb_ipc_open(device, gathered[r][1], C.byref(p)) != 0:
+                    ok = 0
+                    break
+                peers[name] = {"flags": p.value, "inbox_up": p.value + 256, "inbox_dn": p.value + 256 + inbox_bytes}
+        flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 0:
+            return False
+        own = {"flags": base.value, "inbox_up": base.value + 256, "inbox_dn": base.value + 256 + inbox_bytes}
+        self.peer = {"own": own, "peers": peers, "counters": torch.zeros(4, dtype=torch.int32, device=dev),
+                     "epochs": torch.zeros(4, dtype=torch.int64, device=dev), "cap": max_doubles, "lib": lib}
+        return True
+
+    def _exchange_peer(self, x, L: SlabLevel, k: int) -> None:
+        import ctypes as C
+        P = self.peer
+        n = k * L.nr
+        if n > P["cap"]:
+            raise _lib.GsbError("peer halo inbox too small for this exchange")
+        own0, own1 = L.h_top, L.h_top + (L.g1 - L.g0)
+        vp = lambda t: C.c_void_p(t if isinstance(t, int) else t.data_ptr())
+        null = C.c_void_p()
+        up, dn = P["peers"].get("up"), P["peers"].get("dn")
+        has_up, has_dn = bool(L.h_top) and up is not None, bool(L.h_bot) and dn is not None
+        st = C.c_void_p(self.torch.cuda.current_stream().cuda_stream)
+        lib, own = P["lib"], P["own"]
+        _lib.check(lib.gsb_halo_push(vp(x[own0:own0 + k]) if has_up else null, vp(x[own1 - k:own1]) if has_dn else null, n,
+                                     vp(up["inbox_dn"]) if has_up else null, vp(dn["inbox_up"]) if has_dn else null,
+                                     vp(own["flags"]), vp(up["flags"]) if has_up else null,
+                                     vp(dn["flags"]) if has_dn else null, vp(P["counters"]), vp(P["epochs"]), st), "gsb_halo_push")
+        _lib.check(lib.gsb_halo_recv(vp(x[own0 - k:own0]) if has_up else null, vp(x[own1:own1 + k]) if has_dn else null, n,
+                                     vp(own["inbox_up"]) if has_up else null, vp(own["inbox_dn"]) if has_dn else null,
+                                     vp(own["flags"]), vp(up["flags"]) if has_up else null,
+                                     vp(dn["flags"]) if has_dn else null, vp(P["counters"]), vp(P["epochs"]), st), "gsb_halo_recv")
+        self.bytes_sent += (int(has_up) + int(has_dn)) * n * 8
+        self.messages += int(has_up) + int(has_dn)
+
     def _stage(self, t):
         # gloo cannot move CUDA tensors point-to-point: stage through host memory
         return t.cpu() if (self.backend == "gloo" and t.is_cuda) else t
@@ -207,6 +277,8 @@ class SlabComm:
         """Fill the innermost k halo rows on both sides of x from the neighbours' owned rows."""
         if self.world == 1 or k == 0:
             return
+        if getattr(self, "peer", None) is not None and x.is_cuda:
+            return self._exchange_peer(x, L, k)
         dist = self.dist
         ops, recvs = [], []
         own0, own1 = L.h_top, L.h_top + (L.g1 - L.g0)
@@ -267,10 +339,17 @@ class SlabMultigrid:
     ``source`` / ``psi_bc`` are this rank's OWNED rows (``owned_rows()``) of the global arrays."""
 
     def __init__(self, nz: int, nr: int, r_min: float, r_max: float, z_min: float, z_max: float, comm: SlabComm,
-                 ops: Any, *, halo: int = 6, min_rows: int = 32, omega: float = 1.0, pre_smooth: int = 3,
-                 post_smooth: int = 3, min_grid: int = 5):
-        if halo < 2 * min(3, max(pre_smooth, post_smooth)):
-            raise ValueError("halo must cover 2 rows per fused sweep (up to 3 sweeps per pass)")
+                 ops: Any, *, halo: int | None = None, min_rows: int = 32, omega: float = 1.0, pre_smooth: int = 3,
+                 post_smooth: int = 3, min_grid: int = 5, use_graph: bool = True, strict_graph: bool = False):
+        self.use_graph, self.strict_graph, self.used_graph = use_graph, strict_graph, False
+        self._state: dict = {}
+        # one halo exchange per level and V-cycle: the halo must survive the pre-smoothing (2 rows per
+        # sweep become invalid), still hold the 2 rows the residual needs and the 2*post rows the
+        # post-smoothing consumes (those rows receive the prolonged correction redundantly)
+        need = 2 * pre_smooth + max(2, 2 * post_smooth)
+        halo = need if halo is None else halo
+        if halo < need:
+            raise ValueError(f"halo must be >= 2*pre_smooth + max(2, 2*post_smooth) = {need}")
         self.comm, self.ops = comm, ops
         self.omega, self.pre, self.post, self.min_grid, self.halo = omega, pre_smooth, post_smooth, min_grid, halo
         self.levels, self.gathered = plan_slab_levels(nz, nr, r_min, r_max, z_min, z_max, comm.world, comm.rank,
@@ -287,10 +366,10 @@ class SlabMultigrid:
     def _vcycle(self, l: int, x, f):
         L = self.levels[l]
         ops, comm = self.ops, self.comm
-        own0, own1 = L.h_top, L.h_top + (L.g1 - L.g0)
-        comm.exchange(x, L, self.halo)
-        x = ops.smooth(L, x, f, self.omega, self.pre)
-        comm.exchange(x, L, 2)
+        # precondition: x and f hold `halo` valid rows beyond the owned rows (level 0: exchanged by solve();
+        # coarse levels: x starts as zeros everywhere, f = d was exchanged by the caller)
+        x_home = x
+        x = ops.smooth(L, x, f, self.omega, self.pre)  # 2*pre halo rows per side are now invalid
         nzc, nrc = (L.nz + 1) // 2, (L.nr + 1) // 2
         dist_next = l + 1 < len(self.levels)
         if dist_next:
@@ -312,18 +391,21 @@ class SlabMultigrid:
             comm.exchange(d, C, self.halo)  # the halo rows are re-smoothed redundantly and need their rhs
             e = ops.zeros((c_rows, nrc))
             e = self._vcycle(l + 1, e, d)
-            comm.exchange(e, C, 1)
+            comm.exchange(e, C, self.post + 1)  # enough coarse rows to prolong into 2*post fine halo rows
             e_loc, e_row0 = e, c_row0
         else:
             d_full = comm.gather_rows(d, rpr, nzc)
             e_full = ops.coarse_vcycle(self.gathered, d_full, self.omega, self.pre, self.post, self.min_grid)
-            lo, hi = max(0, cg0 - 1), min(nzc, cg1 + 1)
+            lo, hi = max(0, cg0 - self.post - 1), min(nzc, cg1 + self.post + 1)
             e_loc, e_row0 = e_full[lo:hi].contiguous(), lo
             roff = 2 * e_row0 - L.row0
-        fi0, fi1 = max(1, L.g0) - L.row0, min(L.nz - 1, L.g1) - L.row0  # owned fine rows that are not global walls
+        # owned rows plus the 2*post halo rows the post-smoothing will consume (the neighbour adds the same
+        # correction to the same rows: redundant, bit-identical), never global walls
+        ext_top = 2 * self.post if L.h_top else 0
+        ext_bot = 2 * self.post if L.h_bot else 0
+        fi0, fi1 = max(1, L.g0 - ext_top) - L.row0, min(L.nz - 1, L.g1 + ext_bot) - L.row0
         ops.prolong_add(L, x, e_loc, roff, fi0, fi1)
-        comm.exchange(x, L, self.halo)
-        x = ops.smooth(L, x, f, self.omega, self.post)
+        x = ops.smooth(L, x, f, self.omega, self.post, out=x_home)
         return x
 
     def solve(self, source_owned, psi_bc_owned, *, tol: float = 1e-6, max_cycles: int = 500):
@@ -337,26 +419,63 @@ class SlabMultigrid:
         ops, comm = self.ops, self.comm
         n_own = L.g1 - L.g0
         own = slice(L.h_top, L.h_top + n_own)
-        f = ops.zeros((L.rows_loc, L.nr))
-        bc = ops.zeros((L.rows_loc, L.nr))
+        # persistent level-0 buffers: a captured graph (below) refers to their addresses, so repeated
+        # solves on the same SlabMultigrid reuse one graph
+        st = self._state
+        if not st:
+            st["f"], st["bc"], st["x"] = (ops.zeros((L.rows_loc, L.nr)) for _ in range(3))
+            st["graph"] = None
+        f, bc = st["f"], st["bc"]
+        f.zero_()
+        bc.zero_()
         f[own] = ops.from_numpy(np.asarray(source_owned, dtype=np.float64)) if isinstance(source_owned, np.ndarray) else source_owned
         bc[own] = ops.from_numpy(np.asarray(psi_bc_owned, dtype=np.float64)) if isinstance(psi_bc_owned, np.ndarray) else psi_bc_owned
         comm.exchange(f, L, self.halo)
-        x = bc.clone()
+        x = st["x"]
+        x.copy_(bc)
         r0, r1 = max(1, L.g0) - L.row0, min(L.nz - 1, L.g1) - L.row0
-        comm.exchange(x, L, 1)
+        comm.exchange(x, L, self.halo)  # serves the residual (1 row) and the next V-cycle (all rows)
         residual = comm.max(ops.residual_linf(L, x, f, r0, r1))
         cycles = 0
-        while not residual < tol and cycles < max_cycles:
-            x = self._vcycle(0, x, f)
+        def cycle(xc):
+            xc = self._vcycle(0, xc, f)
             # Dirichlet ring (multigrid_solve.py:437-441,458)
-            x[own, 0] = bc[own, 0]
-            x[own, -1] = bc[own, -1]
+            xc[own, 0] = bc[own, 0]
+            xc[own, -1] = bc[own, -1]
             if L.g0 == 0:
-                x[L.h_top] = bc[L.h_top]
+                xc[L.h_top] = bc[L.h_top]
             if L.g1 == L.nz:
-                x[L.h_top + n_own - 1] = bc[L.h_top + n_own - 1]
-            comm.exchange(x, L, 1)
+                xc[L.h_top + n_own - 1] = bc[L.h_top + n_own - 1]
+            comm.exchange(xc, L, self.halo)
+            return xc
+
+        # CUDA graph: the first cycle runs eagerly (it also creates every context and buffer); from the
+        # second cycle on one graph replay issues the whole V-cycle - kernels, halo pushes over peer memory,
+        # the coarse gather - without any host work in between (the host only reads the residual).
+        graph = st["graph"]
+        want_graph = self.use_graph and getattr(x, "is_cuda", False) and graph is None
+        while not residual < tol and cycles < max_cycles:
+            if graph is not None:
+                graph.replay()
+            else:
+                x2 = cycle(x)
+                if x2.data_ptr() != x.data_ptr() if hasattr(x2, "data_ptr") else x2 is not x:
+                    x.copy_(x2)  # multi-launch smoothing phases may end in a pooled buffer
+                if want_graph and cycles == 0:
+                    torch = x.__class__.__module__ and __import__("torch")
+                    torch.cuda.synchronize()
+                    g = torch.cuda.CUDAGraph()
+                    try:
+                        with torch.cuda.graph(g):
+                            x2 = cycle(x)
+                        if x2.data_ptr() == x.data_ptr():
+                            graph = st["graph"] = g
+                    except Exception:
+                        if self.strict_graph:
+                            raise
+                        graph = None
+                    want_graph = graph is not None
             residual = comm.max(ops.residual_linf(L, x, f, r0, r1))
             cycles += 1
-        return x[own], residual, cycles, bool(residual < tol)
+        self.used_graph = graph is not None
+        return x[own].clone(), residual, cycles, bool(residual < tol)

@@ -45,7 +45,7 @@ class NumpySlabOps:
     def _rg(L, rows):
         return np.tile(L.r_row, (rows, 1))
 
-    def smooth(self, L, x, f, omega, sweeps):
+    def smooth(self, L, x, f, omega, sweeps, out=None):
         a = x.numpy()
         rb_sor_smooth_offset(a, f.numpy(), self._rg(L, a.shape[0]), L.dr, L.dz, omega, sweeps, L.row0)
         return x

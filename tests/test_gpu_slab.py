@@ -31,7 +31,7 @@ def _worker(rank, world, port, nz, nr, out_dir):
         torch.cuda.set_device(0)
         src, bc = _problem(nz, nr)
         comm = SlabComm(rank, world)
-        mgs = SlabMultigrid(nz, nr, 4.0, 8.0, -4.0, 4.0, comm, CudaSlabOps(0), halo=6, min_rows=16)
+        mgs = SlabMultigrid(nz, nr, 4.0, 8.0, -4.0, 4.0, comm, CudaSlabOps(0), min_rows=16)
         g0, g1 = mgs.owned_rows()
         psi, res, n, conv = mgs.solve(src[g0:g1], bc[g0:g1], tol=1e-9, max_cycles=30)
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), psi=psi.cpu().numpy(), res=res, n=n, conv=conv, g0=g0, g1=g1,

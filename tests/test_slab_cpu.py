@@ -43,7 +43,7 @@ def _worker(rank, world, port, nz, nr, out_dir):
     try:
         src, bc = _problem(nz, nr)
         comm = SlabComm(rank, world)
-        mgs = SlabMultigrid(nz, nr, 4.0, 8.0, -4.0, 4.0, comm, NumpySlabOps(), halo=6, min_rows=16)
+        mgs = SlabMultigrid(nz, nr, 4.0, 8.0, -4.0, 4.0, comm, NumpySlabOps(), min_rows=16)
         g0, g1 = mgs.owned_rows()
         psi, res, n, conv = mgs.solve(src[g0:g1], bc[g0:g1], tol=1e-9, max_cycles=30)
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), psi=psi.numpy(), res=res, n=n, conv=conv, g0=g0, g1=g1,
@@ -54,7 +54,7 @@ def _worker(rank, world, port, nz, nr, out_dir):
 
 @pytest.mark.parametrize("world", [2, 4])
 def test_slab_solve_equals_single_process_oracle(tmp_path, world):
-    nz, nr = 129, 65
+    nz, nr = (129, 65) if world == 2 else (257, 33)
     port = _free_port()
     mp.spawn(_worker, args=(world, port, nz, nr, str(tmp_path)), nprocs=world, join=True)
     src, bc = _problem(nz, nr)

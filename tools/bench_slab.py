@@ -17,7 +17,11 @@ if world > 1:
     dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
 R = np.linspace(4.0, 8.0, n); Z = np.linspace(-4.0, 4.0, n)
 comm = SlabComm(rank, world)
-mgs = SlabMultigrid(n, n, 4.0, 8.0, -4.0, 4.0, comm, CudaSlabOps(local), halo=6, min_rows=int(os.environ.get("SLAB_MIN_ROWS", "128")))
+peer = False
+if world > 1 and os.environ.get("SLAB_PEER", "1") != "0":
+    peer = comm.enable_peer_halo(local, 12 * n)
+mgs = SlabMultigrid(n, n, 4.0, 8.0, -4.0, 4.0, comm, CudaSlabOps(local), min_rows=int(os.environ.get("SLAB_MIN_ROWS", "128")),
+                    use_graph=os.environ.get("SLAB_GRAPH", "1") != "0", strict_graph=os.environ.get("SLAB_GRAPH_STRICT", "0") == "1")
 g0, g1 = mgs.owned_rows()
 rr, zz = np.meshgrid(R, Z[g0:g1])
 src = -np.exp(-((rr - 6.0) ** 2 + zz ** 2) / 0.5)   # bench_gpu_gs_solver._problem source, psi_bc = 0
@@ -39,7 +43,7 @@ if rank == 0:
     line = {"config": f"{n}x{n} multigrid_solve, slab decomposition", "n_gpus": world, "cycles": cyc, "residual": res,
             "converged": conv, "solve_ms": dt * 1e3, "ms_per_vcycle": dt * 1e3 / max(cyc, 1),
             "glups_per_vcycle": 8.0 * n_int * cyc / dt / 1e9, "levels_distributed": len(mgs.levels),
-            "halo_messages": comm.messages, "halo_mbytes": comm.bytes_sent / 1e6, "psi_sum": chk}
+            "cuda_graph": mgs.used_graph, "halo_transport": "nvlink-peer-kernels" if peer else "nccl-p2p", "halo_messages": comm.messages, "halo_mbytes": comm.bytes_sent / 1e6, "psi_sum": chk}
     if world == 1:
         rr, zz = np.meshgrid(R, Z)
         s = -np.exp(-((rr - 6.0) ** 2 + zz ** 2) / 0.5)
