@@ -453,7 +453,11 @@ class SlabMultigrid:
         # second cycle on one graph replay issues the whole V-cycle - kernels, halo pushes over peer memory,
         # the coarse gather - without any host work in between (the host only reads the residual).
         graph = st["graph"]
-        want_graph = self.use_graph and getattr(x, "is_cuda", False) and graph is None
+        # multi-rank graphs (NCCL gather + spin-wait halo kernels inside one captured graph) hung on the
+        # 2/4-GPU box in round 1 and are therefore opt-in (GSB_SLAB_MULTI_RANK_GRAPH=1) until understood
+        import os as _os
+        multi_ok = comm.world == 1 or _os.environ.get("GSB_SLAB_MULTI_RANK_GRAPH", "0") == "1"
+        want_graph = self.use_graph and multi_ok and getattr(x, "is_cuda", False) and graph is None
         while not residual < tol and cycles < max_cycles:
             if graph is not None:
                 graph.replay()
