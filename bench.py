@@ -115,8 +115,11 @@ def run_reference_arm(args) -> None:
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * float(np.mean(times)), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"UQ sweep of ITER-like {GRID}x{GRID} H-mode equilibria (BASELINE configs[2]), "
-                               f"bounded sample of {n} per step", "grid": [GRID, GRID]},
+        "config": {"workload": f"UQ sweep of {args.batch} independent ITER-like {GRID}x{GRID} H-mode "
+                               "equilibria per GPU (BASELINE configs[2]); coil currents x U(0.85,1.15), "
+                               "Ip x U(0.8,1.2), pedestal params +-3-10 %",
+                   "grid": [GRID, GRID], "batch_per_gpu": args.batch, "method": "picard+multigrid(3,3,omega=1.6)",
+                   "tol": 1e-4, "sample": f"each step solves a bounded sample of {n} of the equilibria on the host cores"},
         "cpu_baseline": {"value": value, "unit": "equilibria/s", "cores": cores, "kind": "port",
                          "sample": f"{n} equilibria per step on a {cores}-process pool (NumPy port of the "
                                    "reference's FusionKernel.solve_equilibrium; the reference is Python and "
