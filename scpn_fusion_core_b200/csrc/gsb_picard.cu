@@ -18,6 +18,8 @@
 constexpr int kPT = 8;   // max partial blocks per equilibrium
 constexpr int kTW = 8;   // doubles per topo partial
 constexpr int kRW = 4;   // doubles per relax partial
+constexpr int kSadChunk = 4096;   // masked points per CTA of the saddle candidate kernel
+constexpr int kSadChunksMax = 64; // -> up to 262144 masked points per equilibrium
 
 struct PicardState {  // SoA, device pointers, [batch_cap] each
   int *active, *status, *iter, *cur, *best, *nxt, *xsel, *seed_active;
@@ -36,6 +38,10 @@ struct gsb_picard_ws {
   double *tpart = nullptr, *spart = nullptr, *rpart = nullptr;
   double *seedJ = nullptr, *cf = nullptr, *mr = nullptr;
   int *rowmask = nullptr;
+  int *mrows = nullptr;        // compact list of the masked (divertor) rows
+  int n_mrows = 0;
+  int cand_chunks = 0;
+  double *cand = nullptr;      // [cap][kSadChunks][16][2] per-chunk smallest |grad psi| candidates (value, flat index)
   int *ints = nullptr;
   double *dbls = nullptr;
   PicardState s{};
@@ -185,6 +191,124 @@ k_xpoint_saddle(Bufs bufs, const int *__restrict__ cur, size_t n, int nz, int nr
     }
     __syncthreads();
     if (prev_i < 0) break;
+  }
+  if (threadIdx.x == 0) xsel[b] = best_i;
+}
+
+// Two-kernel replacement of k_xpoint_saddle for large grids: |grad psi| is evaluated ONCE per masked
+// point.  A: every CTA stages a chunk of masked points' |grad psi| in shared memory and extracts the
+// chunk's 16 smallest in (value, flat index) order (16 block-wide argmin rounds over shared memory,
+// the winner is replaced by +inf).  B: one CTA per equilibrium merges the chunk winners into the
+// global 16 smallest (the same lexicographic order, so ties resolve like the single-CTA kernel) and
+// applies the Hessian saddle test of fusion_kernel.py:295-337.
+__global__ void __launch_bounds__(256)
+k_saddle_cand(Bufs bufs, const int *__restrict__ cur, size_t n, int nz, int nr, GradGeom gg,
+              const int *__restrict__ mrows, int n_mrows, int nchunks, double *__restrict__ cand,
+              const int *__restrict__ active) {
+  __shared__ double sv[kSadChunk];
+  __shared__ double shv[32];
+  __shared__ int shi[32];
+  __shared__ int s_sel;
+  const int b = blockIdx.y, c = blockIdx.x;
+  if (active && !active[b]) return;
+  const double *f = bufs.p[cur ? cur[b] : 0] + (size_t)b * n;
+  const long long total = (long long)n_mrows * nr;
+  const long long i0 = (long long)c * kSadChunk;
+  const int cnt = (int)max(0LL, min((long long)kSadChunk, total - i0));
+  for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+    const long long idx = i0 + i;
+    const int mr = (int)(idx / nr), ir = (int)(idx - (long long)mr * nr);
+    const int iz = mrows[mr];
+    double gz, gr;
+    grad_point(f, nz, nr, iz, ir, gg, gz, gr);
+    const double bm = hypot_glibc(gr, gz);
+    sv[i] = isfinite(bm) ? bm : INFINITY;
+  }
+  __syncthreads();
+  double *o = cand + (((size_t)b * nchunks + c) * 16) * 2;
+  for (int round = 0; round < 16; ++round) {
+    ValIdx m{0.0, -1};
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+      const double v = sv[i];
+      if (v < INFINITY && (m.i < 0 || v < m.v)) m = ValIdx{v, i};  // strided ascending i: first minimum wins
+    }
+    m = block_arg<false>(m, shv, shi);
+    if (threadIdx.x == 0) {
+      s_sel = m.i;
+      if (m.i >= 0) {
+        const long long idx = i0 + m.i;
+        const int mr = (int)(idx / nr), ir = (int)(idx - (long long)mr * nr);
+        o[2 * round] = m.v;
+        o[2 * round + 1] = (double)(mrows[mr] * nr + ir);
+        sv[m.i] = INFINITY;
+      } else {
+        o[2 * round] = INFINITY;
+        o[2 * round + 1] = -1.0;
+      }
+    }
+    __syncthreads();
+    if (s_sel < 0) {  // chunk exhausted: fill the rest
+      for (int r = round + 1 + threadIdx.x; r < 16; r += blockDim.x) {
+        o[2 * r] = INFINITY;
+        o[2 * r + 1] = -1.0;
+      }
+      break;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_saddle_pick(Bufs bufs, const int *__restrict__ cur, size_t n, int nz, int nr, double dr2, double dz2,
+              double four_drdz, int nchunks, double *__restrict__ cand, int *__restrict__ xsel,
+              const int *__restrict__ active) {
+  __shared__ double shv[32];
+  __shared__ int shi[32];
+  __shared__ int s_sel;
+  __shared__ double best_v;
+  __shared__ int best_i;
+  const int b = blockIdx.x;
+  if (active && !active[b]) return;
+  const double *f = bufs.p[cur ? cur[b] : 0] + (size_t)b * n;
+  double *cv = cand + (size_t)b * nchunks * 32;
+  const int ncand = nchunks * 16;
+  if (threadIdx.x == 0) {
+    best_v = INFINITY;
+    best_i = -1;
+  }
+  __syncthreads();
+  for (int round = 0; round < 16; ++round) {
+    // global (value, flat index) minimum of the remaining candidates
+    double mv = INFINITY;
+    int mf = -1, mslot = -1;
+    for (int i = threadIdx.x; i < ncand; i += blockDim.x) {
+      const double v = cv[2 * i];
+      const int fl = (int)cv[2 * i + 1];
+      if (fl < 0) continue;
+      if (mslot < 0 || v < mv || (v == mv && fl < mf)) mv = v, mf = fl, mslot = i;
+    }
+    // reduce on (value, flat): block_arg breaks ties on the index field -> carry the flat index there
+    ValIdx m = block_arg<false>(ValIdx{mv, mf}, shv, shi);
+    if (threadIdx.x == 0) s_sel = m.i;
+    __syncthreads();
+    const int sel = s_sel;
+    if (sel < 0) break;
+    if (mf == sel && mslot >= 0) cv[2 * mslot + 1] = -1.0;  // the owning thread retires the winner (flat indices are unique)
+    if (threadIdx.x == 0) {
+      const int iz = sel / nr, ir = sel - iz * nr;
+      if (iz > 0 && iz < nz - 1 && ir > 0 && ir < nr - 1) {
+        const double *q = f + sel;
+        const double c2 = dmul(2.0, q[0]);
+        const double d2r = __ddiv_rn(dadd(dsub(q[1], c2), q[-1]), dr2);
+        const double d2z = __ddiv_rn(dadd(dsub(q[nr], c2), q[-nr]), dz2);
+        const double drz = __ddiv_rn(dadd(dsub(dsub(q[nr + 1], q[nr - 1]), q[-nr + 1]), q[-nr - 1]), four_drdz);
+        const double det = dsub(dmul(d2r, d2z), dmul(drz, drz));
+        if (isfinite(det) && det < 0.0 && m.v < best_v) {
+          best_v = m.v;
+          best_i = sel;
+        }
+      }
+    }
+    __syncthreads();
   }
   if (threadIdx.x == 0) xsel[b] = best_i;
 }
@@ -1281,6 +1405,7 @@ static int picard_ws_ensure(gsb_ctx *ctx, const gsb_picard_params *p) {
     GSB_CUDA(cudaMalloc(&w->cf, ctx->nr * sizeof(double)));
     GSB_CUDA(cudaMalloc(&w->mr, ctx->nr * sizeof(double)));
     GSB_CUDA(cudaMalloc(&w->rowmask, ctx->nz * sizeof(int)));
+    GSB_CUDA(cudaMalloc(&w->mrows, ctx->nz * sizeof(int)));
     GSB_CUDA(cudaMalloc(&w->ints, (size_t)w->cap * 8 * sizeof(int)));
     GSB_CUDA(cudaMalloc(&w->dbls, (size_t)w->cap * (5 + 2 + 8) * sizeof(double)));
     const size_t c = w->cap;
@@ -1331,6 +1456,13 @@ static int picard_ws_ensure(gsb_ctx *ctx, const gsb_picard_params *p) {
     GSB_CUDA(cudaMemcpy(w->cf, cf.data(), nr * sizeof(double), cudaMemcpyHostToDevice));
     GSB_CUDA(cudaMemcpy(w->mr, mr.data(), nr * sizeof(double), cudaMemcpyHostToDevice));
     GSB_CUDA(cudaMemcpy(w->rowmask, mask.data(), nz * sizeof(int), cudaMemcpyHostToDevice));
+    {
+      std::vector<int> rows;
+      for (int i = 0; i < nz; ++i)
+        if (mask[i]) rows.push_back(i);
+      w->n_mrows = (int)rows.size();
+      if (!rows.empty()) GSB_CUDA(cudaMemcpy(w->mrows, rows.data(), rows.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
     GSB_CUDA(cudaMemcpy(w->seedJ, seed.data(), seed.size() * sizeof(double), cudaMemcpyHostToDevice));
     w->mu0 = p->mu0;
     w->z_min = p->z_min;
@@ -1357,6 +1489,31 @@ static ProfileDev to_dev(const gsb_profile &q) {
     d.f[i] = q.ped_ff[i];
   }
   return d;
+}
+
+// X-point saddle filter for the streaming path: two-kernel candidate selection when the masked region
+// fits kSadChunksMax chunks, the single-CTA kernel otherwise.
+static int saddle_launch(gsb_ctx *ctx, Bufs bufs, const int *cur, int batch, const GradGeom &gg, double dr2,
+                         double dz2, double four_drdz, int *xsel, const int *active, cudaStream_t st) {
+  gsb_picard_ws *w = ctx->picard;
+  const long long total = (long long)w->n_mrows * ctx->nr;
+  const int nchunks = (int)((total + kSadChunk - 1) / kSadChunk);
+  if (nchunks < 1 || nchunks > kSadChunksMax) {
+    k_xpoint_saddle<<<batch, 256, 0, st>>>(bufs, cur, ctx->n, ctx->nz, ctx->nr, gg, dr2, dz2, four_drdz, w->rowmask, xsel, active);
+    GSB_LAUNCH_CHECK();
+    return GSB_OK;
+  }
+  if (!w->cand || w->cand_chunks < nchunks) {
+    if (w->cand) cudaFree(w->cand);
+    w->cand = nullptr;
+    GSB_CUDA(cudaMalloc(&w->cand, (size_t)w->cap * nchunks * 32 * sizeof(double)));
+    w->cand_chunks = nchunks;
+  }
+  k_saddle_cand<<<dim3(nchunks, batch), 256, 0, st>>>(bufs, cur, ctx->n, ctx->nz, ctx->nr, gg, w->mrows, w->n_mrows, nchunks, w->cand, active);
+  GSB_LAUNCH_CHECK();
+  k_saddle_pick<<<batch, 256, 0, st>>>(bufs, cur, ctx->n, ctx->nz, ctx->nr, dr2, dz2, four_drdz, nchunks, w->cand, xsel, active);
+  GSB_LAUNCH_CHECK();
+  return GSB_OK;
 }
 
 // Persistent resident solve (k_picard_resident).  Returns GSB_ESTATE (without setting an error) when
@@ -1463,7 +1620,7 @@ void gsb_picard_ws_free(gsb_ctx *ctx) {
   gsb_picard_ws *w = ctx->picard;
   if (!w) return;
   void *ptrs[] = {w->buf1, w->buf2, w->W, w->source, w->ring, w->tpart, w->spart, w->rpart,
-                  w->seedJ, w->cf, w->mr, w->rowmask, w->ints, w->dbls, w->res_ws};
+                  w->seedJ, w->cf, w->mr, w->rowmask, w->ints, w->dbls, w->res_ws, w->mrows, w->cand};
   for (void *q : ptrs)
     if (q) cudaFree(q);
   delete w;
@@ -1496,8 +1653,8 @@ int gsb_topology(gsb_ctx *ctx, const double *psi_dev, int batch, double z_min, i
   GSB_LAUNCH_CHECK();
   if (saddle) {
     volatile double dr2 = ctx->dr * ctx->dr, dz2 = ctx->dz * ctx->dz, f1 = 4.0 * ctx->dr, f2 = f1 * ctx->dz;
-    k_xpoint_saddle<<<batch, 256, 0, st>>>(bufs, nullptr, ctx->n, ctx->nz, ctx->nr, gg, dr2, dz2, f2, w->rowmask, w->s.xsel, nullptr);
-    GSB_LAUNCH_CHECK();
+    rc = saddle_launch(ctx, bufs, nullptr, batch, gg, dr2, dz2, f2, w->s.xsel, nullptr, st);
+    if (rc) return rc;
   }
   k_topo_final<<<(batch + 127) / 128, 128, 0, st>>>(bufs, nullptr, ctx->n, ctx->nr, P, w->tpart,
                                                     saddle ? w->s.xsel : nullptr, out_dev, nullptr, 0, batch, nullptr);
@@ -1607,8 +1764,8 @@ int gsb_picard_solve(gsb_ctx *ctx, const gsb_picard_params *p, double *psi_dev, 
     k_topo<<<dim3(P, batch), 256, 0, st>>>(bufs, s.cur, n, nz, nr, gg, w->rowmask, w->tpart, s.active);
     GSB_LAUNCH_CHECK();
     if (p->saddle) {
-      k_xpoint_saddle<<<batch, 256, 0, st>>>(bufs, s.cur, n, nz, nr, gg, dr2, dz2, f2, w->rowmask, s.xsel, s.active);
-      GSB_LAUNCH_CHECK();
+      rc = saddle_launch(ctx, bufs, s.cur, batch, gg, dr2, dz2, f2, s.xsel, s.active, st);
+      if (rc) return rc;
     }
     k_topo_final<<<(batch + 127) / 128, 128, 0, st>>>(bufs, s.cur, n, nr, P, w->tpart, p->saddle ? s.xsel : nullptr,
                                                       s.topo, s.axbnd, 1, batch, s.active);
