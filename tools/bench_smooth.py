@@ -17,7 +17,10 @@ for nz, nr, B in cases:
     src = torch.randn((B, nz, nr), dtype=torch.float64, device="cuda")
     st = D.stream_ptr()
     n_int = (nz - 2) * (nr - 2)
+    only = os.environ.get("FUSE_ONLY")
     for fuse, sweeps in ((0, 6), (1, 6), (2, 6), (3, 6)):
+        if only is not None and int(only) != fuse:
+            continue
         _lib.check(ctx.lib.gsb_smooth_ex(ctx.handle, D.ptr(psi), D.ptr(src), B, 1.3, sweeps, 0, fuse, st))
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
