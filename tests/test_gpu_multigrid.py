@@ -228,3 +228,21 @@ def test_fused_sweeps_equal_per_colour_passes(mg, shape, batch):
     if nz * nr <= 300 * 700:
         o = G.rb_sor_smooth(psi[0].copy(), src[0], rg, dr, dz, 1.3, 3)
         np.testing.assert_array_equal(mg.mg_smooth(psi[0].copy(), src[0], rg, dr, dz, 1.3, 3), o)
+
+
+@pytest.mark.parametrize("shape", [(3, 3), (4, 7), (5, 64), (6, 65), (33, 33), (64, 64), (128, 128), (7, 130)])
+def test_fused_sweeps_small_and_even_grids_vs_oracle(mg, shape):
+    """Edge shapes of the temporally blocked kernel (fewer rows than the pipeline depth, even sizes, exactly
+    one 64-column strip, one column more than a strip) against the oracle, bit-exact."""
+    nz, nr = shape
+    rng = np.random.default_rng(nz * 131 + nr)
+    R = np.linspace(0.5, 2.5, nr)
+    rg = np.tile(R, (nz, 1))
+    dr, dz = float(R[1] - R[0]), 1.0 / max(nz - 1, 1)
+    psi = rng.normal(size=(nz, nr))
+    src = rng.normal(size=(nz, nr))
+    for sweeps in (1, 2, 3, 4, 7):
+        ref = G.rb_sor_smooth(psi.copy(), src, rg, dr, dz, 1.7, sweeps)
+        for fuse in (0, 1, 3):
+            out = mg.mg_smooth(psi.copy(), src, rg, dr, dz, 1.7, sweeps, fuse=fuse)
+            np.testing.assert_array_equal(out, ref, err_msg=f"shape={shape} sweeps={sweeps} fuse={fuse}")
