@@ -21,3 +21,11 @@ else:
     r = bk.solve(cc, ip, ped, ped, to_host=False)
 torch.cuda.synchronize()
 print("iterations", r["iterations"].mean())
+import time
+torch.cuda.synchronize(); t0 = time.perf_counter()
+if saddle:
+    r = bk.solve(cc, to_host=False)
+else:
+    r = bk.solve(cc, ip, ped, ped, to_host=False)
+torch.cuda.synchronize(); dt = time.perf_counter() - t0
+print(f"n={n} B={B} saddle={saddle}: {dt*1e3:.1f} ms = {B/dt:.0f} eq/s, iterations {r['iterations'].mean():.1f}, converged {int(r['converged'].sum())}")
