@@ -316,7 +316,7 @@ def run_gpu_arm(args) -> None:
         torch.cuda.synchronize()
         return f0.elapsed_time(f1) / reps
 
-    s_ms = time_smooth(3, 3, 10)             # one launch: 3 sweeps
+    s_ms = time_smooth(3, 6, 5) / 2.0        # per launch (3 sweeps each); two launches per call, back to back
     c_ms = time_smooth(0, 3, 10) / 6.0       # per colour-pass launch
     s_bytes = 24.0 * n_int * B * 3           # 24 B/LUP per sweep x 3 sweeps per launch
     s_achieved = s_bytes / (s_ms * 1e-3) / 1e9
