@@ -246,3 +246,27 @@ def test_fused_sweeps_small_and_even_grids_vs_oracle(mg, shape):
         for fuse in (0, 1, 3):
             out = mg.mg_smooth(psi.copy(), src, rg, dr, dz, 1.7, sweeps, fuse=fuse)
             np.testing.assert_array_equal(out, ref, err_msg=f"shape={shape} sweeps={sweeps} fuse={fuse}")
+
+
+@pytest.mark.parametrize("shape", [(200, 300), (257, 129), (130, 515)])
+def test_vcycle_multi_tile_levels_vs_oracle(mg, shape):
+    """V-cycles whose finest levels span several 64-column strips (out-of-place fused sweeps with the
+    ping-pong partner buffers), even and odd level sizes, batch of 2: bit-identical to the oracle."""
+    import torch
+    nz, nr = shape
+    rng = np.random.default_rng(nz + 7 * nr)
+    R = np.linspace(1.5, 4.5, nr)
+    rg = np.tile(R, (nz, 1))
+    dr, dz = float(R[1] - R[0]), 3.0 / (nz - 1)
+    psi = rng.normal(size=(2, nz, nr))
+    src = rng.normal(size=(2, nz, nr))
+    out = mg.multigrid_vcycle(torch.tensor(psi, device="cuda"), torch.tensor(src, device="cuda"), rg, dr, dz,
+                              omega=1.4, pre_smooth=3, post_smooth=3).cpu().numpy()
+    for b in range(2):
+        ref = G.vcycle(psi[b], src[b], rg, dr, dz, omega=1.4, pre=3, post=3, min_grid=5)
+        np.testing.assert_array_equal(out[b], ref, err_msg=f"shape={shape} b={b}")
+    # a second cycle from the first one's output, odd smoothing counts (multi-launch ping-pong parity)
+    out2 = mg.multigrid_vcycle(torch.tensor(out[0], device="cuda"), torch.tensor(src[0], device="cuda"), rg, dr, dz,
+                               omega=1.4, pre_smooth=4, post_smooth=2).cpu().numpy()
+    ref2 = G.vcycle(out[0], src[0], rg, dr, dz, omega=1.4, pre=4, post=2, min_grid=5)
+    np.testing.assert_array_equal(out2, ref2)
