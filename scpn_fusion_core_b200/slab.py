@@ -245,6 +245,21 @@ class SlabComm:
                      "epochs": torch.zeros(4, dtype=torch.int64, device=dev), "cap": max_doubles, "lib": lib}
         return True
 
+    def disable_peer_halo(self) -> None:
+        """Unmap the neighbours' IPC blocks and free this rank's (collective in spirit: call it on every rank
+        once no exchange is in flight; NCCL point-to-point exchanges take over again)."""
+        P = getattr(self, "peer", None)
+        if P is None:
+            return
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier(group=self.group)  # nobody may still be pushing into a block that is unmapped below
+        import ctypes as C
+        for nb in P["peers"].values():
+            P["lib"].gsb_ipc_close(C.c_void_p(nb["flags"]))
+        P["lib"].gsb_ipc_free(C.c_void_p(P["own"]["flags"]))
+        self.peer = None
+
     def _exchange_peer(self, x, L: SlabLevel, k: int) -> None:
         import ctypes as C
         P = self.peer
@@ -466,7 +481,7 @@ class SlabMultigrid:
                 if x2.data_ptr() != x.data_ptr() if hasattr(x2, "data_ptr") else x2 is not x:
                     x.copy_(x2)  # multi-launch smoothing phases may end in a pooled buffer
                 if want_graph and cycles == 0:
-                    torch = x.__class__.__module__ and __import__("torch")
+                    import torch
                     torch.cuda.synchronize()
                     g = torch.cuda.CUDAGraph()
                     try:

@@ -56,4 +56,5 @@ if rank == 0:
                                               "bit_identical": bool(torch.equal(p, psi))}
     print(json.dumps(line), flush=True)
 if world > 1:
+    comm.disable_peer_halo()
     dist.destroy_process_group()
