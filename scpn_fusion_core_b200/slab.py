@@ -116,6 +116,7 @@ class CudaSlabOps:
         self.torch = D.torch_mod()
         self._ctx: dict = {}
         self._alt: dict = {}
+        self._linf_out = None
 
     def zeros(self, shape):
         return self.D.zeros(shape, self.device)
@@ -177,20 +178,26 @@ class CudaSlabOps:
     def residual_linf(self, L: SlabLevel, x, f, row0: int, row1: int) -> float:
         D = self.D
         ctx = self._context(L)
-        out = D.zeros((1,), self.device)
+        out = self._linf_out
+        if out is None:
+            out = self._linf_out = D.zeros((1,), self.device)
+        out.zero_()
         _lib.check(ctx.lib.gsb_slab_residual_linf(ctx.handle, D.ptr(x), D.ptr(f), row0, row1, D.ptr(out),
                                                   D.stream_ptr()), "gsb_slab_residual_linf")
         return float(out.item())
 
     def coarse_vcycle(self, G: dict, d_full, omega: float, pre: int, post: int, min_grid: int):
-        """The replicated tail of the V-cycle on the gathered level (zero initial guess)."""
-        from . import multigrid_solve as mg
-        import importlib
-        mgm = importlib.import_module(__package__ + ".multigrid_solve")
-        rg = np.tile(G["r_row"], (G["nz"], 1))
+        """The replicated tail of the V-cycle on the gathered level (zero initial guess): one gsb_vcycle
+        call on a cached context of that level's geometry (multigrid_solve.py:252-335 from level `G`)."""
+        D = self.D
+        key = ("coarse", G["nz"], G["nr"], G["dr"], G["dz"])
+        ctx = self._ctx.get(key)
+        if ctx is None:
+            ctx = self._ctx[key] = D.Context(G["nz"], G["nr"], G["r_row"], None, G["dr"], G["dz"], 1, self.device)
         x0 = self.torch.zeros_like(d_full)
-        return mgm.multigrid_vcycle(x0, d_full, rg, G["dr"], G["dz"], omega=omega, pre_smooth=pre, post_smooth=post,
-                                    min_grid=min_grid)
+        _lib.check(ctx.lib.gsb_vcycle(ctx.handle, D.ptr(x0), D.ptr(d_full), 1, omega, int(pre), int(post), int(min_grid),
+                                      D.stream_ptr()), "gsb_vcycle")
+        return x0
 
 
 class SlabComm:
