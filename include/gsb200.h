@@ -267,6 +267,33 @@ int gsb_halo_recv(double *halo_up, double *halo_dn, long long n, const double *i
                   long long *flags_local, long long *flags_up, long long *flags_dn, int *counters, long long *epochs,
                   void *stream);
 
+/* Native driver of the distributed levels of one slab V-cycle: every launch of the descent
+ * (gsb_slab_down) and of the ascent (gsb_slab_up) is issued from one call; the host gathers the
+ * coarsest distributed right-hand side and runs the replicated coarse V-cycle in between. */
+typedef struct gsb_slab_level_desc {
+  gsb_ctx *ctx;              /* slab context of the level (rows_loc x nr) */
+  double *x, *f, *alt, *cur; /* solution, right-hand side, ping-pong partner (NULL if single tile), live buffer */
+  int rows_loc, nr;
+  int own0, own1;            /* owned local rows [own0, own1) */
+  int has_up, has_dn;        /* neighbours present */
+  int row0;                  /* global row of local row 0 (colour parity) */
+  int roff, ci0, ci1;        /* restriction target: fine local row = 2*coarse local row + roff; rows to compute */
+  int nzc_loc, nrc;          /* shape of the restriction target (next level's f, or the gathered level's owned rows) */
+  int fi0, fi1;              /* fine local rows that receive the prolonged correction */
+} gsb_slab_level_desc;
+typedef struct gsb_slab_halo_desc {
+  double *inbox_up, *inbox_dn;        /* this rank's inboxes */
+  double *up_inbox_dn, *dn_inbox_up;  /* the neighbours' inboxes (peer pointers) */
+  long long *flags_local, *flags_up, *flags_dn;
+  int *counters;
+  long long *epochs;
+  long long cap;                      /* doubles per inbox */
+} gsb_slab_halo_desc;
+int gsb_slab_down(gsb_slab_level_desc *lev, int nlev, double *d_last, const gsb_slab_halo_desc *halo, int halo_rows,
+                  double omega, int pre, void *stream);
+int gsb_slab_up(gsb_slab_level_desc *lev, int nlev, const double *e_last, int nze_last_loc, int roff_last,
+                const gsb_slab_halo_desc *halo, int e_rows, double omega, int post, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -80,6 +80,8 @@ SIGNATURES = {
                               c_void_p, c_void_p]),
     "gsb_halo_recv": (c_int, [c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                               c_void_p, c_void_p]),
+    "gsb_slab_down": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_double, c_int, c_void_p]),
+    "gsb_slab_up": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_double, c_int, c_void_p]),
     "gsb_slab_single_tile": (c_int, [c_void_p, c_int]),
     "gsb_slab_smooth": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_int, c_int, c_void_p]),
     "gsb_slab_residual_restrict": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,

@@ -331,4 +331,98 @@ int gsb_slab_residual_linf(gsb_ctx *ctx, const double *x_dev, const double *src_
   return GSB_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Native V-cycle driver for the distributed levels: every launch of the descent (pre-smoothing,
+// residual + restriction, halo exchange of the coarse right-hand side) and of the ascent (halo exchange
+// of the coarse correction, prolongation, post-smoothing) is issued from ONE call each, instead of ~25
+// host round trips per level from Python.  The gather + replicated coarse solve happens between the two
+// calls on the host side.  Halos travel through gsb_halo_push/recv (halo == NULL: single rank).
+// ------------------------------------------------------------------------------------------
+static int slab_exchange(const gsb_slab_halo_desc *h, double *a, const gsb_slab_level_desc &L, int k, void *stream) {
+  if (!h || k <= 0 || (!L.has_up && !L.has_dn)) return GSB_OK;
+  const long long n = (long long)k * L.nr;
+  GSB_REQUIRE(n <= h->cap, "slab exchange: inbox too small");
+  GSB_REQUIRE(L.own1 - L.own0 >= k, "slab exchange: fewer owned rows than halo rows");
+  int rc = gsb_halo_push(L.has_up ? a + (size_t)L.own0 * L.nr : nullptr, L.has_dn ? a + (size_t)(L.own1 - k) * L.nr : nullptr, n,
+                         L.has_up ? h->up_inbox_dn : nullptr, L.has_dn ? h->dn_inbox_up : nullptr, h->flags_local,
+                         L.has_up ? h->flags_up : nullptr, L.has_dn ? h->flags_dn : nullptr, h->counters, h->epochs, stream);
+  if (rc) return rc;
+  return gsb_halo_recv(L.has_up ? a + (size_t)(L.own0 - k) * L.nr : nullptr, L.has_dn ? a + (size_t)L.own1 * L.nr : nullptr, n,
+                       L.has_up ? h->inbox_up : nullptr, L.has_dn ? h->inbox_dn : nullptr, h->flags_local,
+                       L.has_up ? h->flags_up : nullptr, L.has_dn ? h->flags_dn : nullptr, h->counters, h->epochs, stream);
+}
+
+// `sweeps` sweeps from *cur (ping-pong between x and alt when the level is multi-tile); *cur follows the data
+static int slab_smooth_pp(gsb_slab_level_desc &L, double **cur, double omega, int sweeps, void *stream) {
+  int left = sweeps;
+  while (left > 0) {
+    const int s = left < 3 ? left : 3;
+    double *dst = *cur;
+    if (!gsb_slab_single_tile(L.ctx, s)) {
+      dst = (*cur == L.x) ? L.alt : L.x;
+      GSB_REQUIRE(dst != nullptr, "slab level needs an alternate buffer (multi-tile sweep)");
+    }
+    int rc = gsb_slab_smooth(L.ctx, *cur, dst, L.f, omega, s, L.row0, stream);
+    if (rc) return rc;
+    *cur = dst;
+    left -= s;
+  }
+  return GSB_OK;
+}
+
+int gsb_slab_down(gsb_slab_level_desc *lev, int nlev, double *d_last, const gsb_slab_halo_desc *halo, int halo_rows,
+                  double omega, int pre, void *stream) {
+  GSB_REQUIRE(lev && nlev >= 1 && d_last, "gsb_slab_down: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int l = 0; l < nlev; ++l) {
+    gsb_slab_level_desc &L = lev[l];
+    double *cur = L.x;
+    int rc = slab_smooth_pp(L, &cur, omega, pre, stream);
+    if (rc) return rc;
+    L.cur = cur;
+    double *d = (l + 1 < nlev) ? lev[l + 1].f : d_last;
+    GSB_CUDA(cudaMemsetAsync(d, 0, (size_t)L.nzc_loc * L.nrc * sizeof(double), st));
+    rc = gsb_slab_residual_restrict(L.ctx, cur, L.f, d, L.nzc_loc, L.nrc, L.roff, L.ci0, L.ci1, stream);
+    if (rc) return rc;
+    if (l + 1 < nlev) {
+      gsb_slab_level_desc &C = lev[l + 1];
+      rc = slab_exchange(halo, C.f, C, halo_rows, stream);  // the halo rows are re-smoothed redundantly
+      if (rc) return rc;
+      GSB_CUDA(cudaMemsetAsync(C.x, 0, (size_t)C.rows_loc * C.nr * sizeof(double), st));
+    }
+  }
+  return GSB_OK;
+}
+
+int gsb_slab_up(gsb_slab_level_desc *lev, int nlev, const double *e_last, int nze_last_loc, int roff_last,
+                const gsb_slab_halo_desc *halo, int e_rows, double omega, int post, void *stream) {
+  GSB_REQUIRE(lev && nlev >= 1 && e_last, "gsb_slab_up: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int l = nlev - 1; l >= 0; --l) {
+    gsb_slab_level_desc &L = lev[l];
+    double *cur = L.cur ? L.cur : L.x;
+    const double *e = e_last;
+    int roff = roff_last, nze = nze_last_loc;
+    if (l + 1 < nlev) {
+      gsb_slab_level_desc &C = lev[l + 1];
+      int rc = slab_exchange(halo, C.x, C, e_rows, stream);  // C.cur == C.x after its post-smoothing
+      if (rc) return rc;
+      e = C.x;
+      roff = L.roff;
+      nze = L.nzc_loc;
+    }
+    int rc = gsb_slab_prolong_add(L.ctx, e, nze, L.nrc, cur, roff, L.fi0, L.fi1, stream);
+    if (rc) return rc;
+    rc = slab_smooth_pp(L, &cur, omega, post, stream);
+    if (rc) return rc;
+    if (cur != L.x) {  // odd number of out-of-place passes: bring the level home
+      GSB_CUDA(cudaMemcpyAsync(L.x, cur, (size_t)L.rows_loc * L.nr * sizeof(double), cudaMemcpyDeviceToDevice, st));
+      cur = L.x;
+    }
+    L.cur = L.x;
+  }
+  return GSB_OK;
+}
+
 }  // extern "C"

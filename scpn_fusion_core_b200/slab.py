@@ -31,6 +31,18 @@ import numpy as np
 from . import _lib
 
 
+class _LevelDesc(ctypes.Structure):  # gsb_slab_level_desc (include/gsb200.h)
+    _fields_ = [("ctx", ctypes.c_void_p), ("x", ctypes.c_void_p), ("f", ctypes.c_void_p), ("alt", ctypes.c_void_p),
+                ("cur", ctypes.c_void_p)] + [(n, ctypes.c_int) for n in (
+                    "rows_loc", "nr", "own0", "own1", "has_up", "has_dn", "row0", "roff", "ci0", "ci1", "nzc_loc", "nrc",
+                    "fi0", "fi1")]
+
+
+class _HaloDesc(ctypes.Structure):  # gsb_slab_halo_desc
+    _fields_ = [(n, ctypes.c_void_p) for n in ("inbox_up", "inbox_dn", "up_inbox_dn", "dn_inbox_up", "flags_local",
+                                                "flags_up", "flags_dn", "counters", "epochs")] + [("cap", ctypes.c_longlong)]
+
+
 @dataclass
 class SlabLevel:
     """One distributed level as seen by one rank."""
@@ -364,6 +376,9 @@ class SlabMultigrid:
                  ops: Any, *, halo: int | None = None, min_rows: int = 32, omega: float = 1.0, pre_smooth: int = 3,
                  post_smooth: int = 3, min_grid: int = 5, use_graph: bool = True, strict_graph: bool = False):
         self.use_graph, self.strict_graph, self.used_graph = use_graph, strict_graph, False
+        import os as _os
+        self.use_native = _os.environ.get("GSB_SLAB_NATIVE", "1") != "0"  # C driver of the distributed levels
+        self._native = None
         self._state: dict = {}
         # one halo exchange per level and V-cycle: the halo must survive the pre-smoothing (2 rows per
         # sweep become invalid), still hold the 2 rows the residual needs and the 2*post rows the
@@ -430,6 +445,81 @@ class SlabMultigrid:
         x = ops.smooth(L, x, f, self.omega, self.post, out=x_home)
         return x
 
+    # ---- native driver: all launches of the distributed levels from two C calls per V-cycle ----
+    def _coarse_geometry(self, l: int):
+        """(c_rows, c_row0, cg0, cg1, nzc, nrc) of the array that level l restricts into."""
+        L, comm = self.levels[l], self.comm
+        nzc, nrc = (L.nz + 1) // 2, (L.nr + 1) // 2
+        if l + 1 < len(self.levels):
+            C = self.levels[l + 1]
+            return C.rows_loc, C.row0, C.g0, C.g1, nzc, nrc
+        rpr = self.gathered["rows_per_rank"]
+        cg0 = comm.rank * rpr
+        cg1 = (comm.rank + 1) * rpr + (1 if comm.rank == comm.world - 1 else 0)
+        return cg1 - cg0, cg0, cg0, cg1, nzc, nrc
+
+    def _native_setup(self, x0, f0) -> bool:
+        ops, comm = self.ops, self.comm
+        if not isinstance(ops, CudaSlabOps) or not self.use_native:
+            return False
+        if comm.world > 1 and getattr(comm, "peer", None) is None:
+            return False  # NCCL point-to-point exchanges are issued from Python
+        D, lib = ops.D, _lib.load()
+        n = len(self.levels)
+        descs = (_LevelDesc * n)()
+        keep = []
+        for l, L in enumerate(self.levels):
+            ctx = ops._context(L)
+            x = x0 if l == 0 else ops.zeros((L.rows_loc, L.nr))
+            f = f0 if l == 0 else ops.zeros((L.rows_loc, L.nr))
+            single = all(lib.gsb_slab_single_tile(ctx.handle, s) for s in (1, 2, 3))
+            alt = None if single else D.empty((L.rows_loc, L.nr), ops.device)
+            c_rows, c_row0, cg0, cg1, nzc, nrc = self._coarse_geometry(l)
+            ext_top = 2 * self.post if L.h_top else 0
+            ext_bot = 2 * self.post if L.h_bot else 0
+            d = descs[l]
+            d.ctx, d.x, d.f = ctx.handle.value if hasattr(ctx.handle, "value") else ctx.handle, x.data_ptr(), f.data_ptr()
+            d.alt, d.cur = (alt.data_ptr() if alt is not None else None), x.data_ptr()
+            d.rows_loc, d.nr, d.own0, d.own1 = L.rows_loc, L.nr, L.h_top, L.h_top + (L.g1 - L.g0)
+            d.has_up, d.has_dn, d.row0 = int(bool(L.h_top)), int(bool(L.h_bot)), L.row0
+            d.roff, d.ci0, d.ci1 = 2 * c_row0 - L.row0, max(1, cg0) - c_row0, min(nzc - 1, cg1) - c_row0
+            d.nzc_loc, d.nrc = c_rows, nrc
+            d.fi0, d.fi1 = max(1, L.g0 - ext_top) - L.row0, min(L.nz - 1, L.g1 + ext_bot) - L.row0
+            keep += [ctx, x, f, alt]
+        c_rows, c_row0, cg0, cg1, nzc, nrc = self._coarse_geometry(n - 1)
+        d_last = ops.zeros((c_rows, nrc))
+        lo, hi = max(0, cg0 - self.post - 1), min(nzc, cg1 + self.post + 1)
+        halo = None
+        if comm.world > 1:
+            P = comm.peer
+            up, dn = P["peers"].get("up"), P["peers"].get("dn")
+            halo = _HaloDesc()
+            halo.inbox_up, halo.inbox_dn = P["own"]["inbox_up"], P["own"]["inbox_dn"]
+            halo.up_inbox_dn = up["inbox_dn"] if up else None
+            halo.dn_inbox_up = dn["inbox_up"] if dn else None
+            halo.flags_local = P["own"]["flags"]
+            halo.flags_up = up["flags"] if up else None
+            halo.flags_dn = dn["flags"] if dn else None
+            halo.counters, halo.epochs, halo.cap = P["counters"].data_ptr(), P["epochs"].data_ptr(), P["cap"]
+        self._native = {"descs": descs, "keep": keep, "d_last": d_last, "lo": lo, "hi": hi, "nzc": nzc,
+                        "roff_last": 2 * lo - self.levels[-1].row0, "halo": halo, "lib": lib}
+        return True
+
+    def _vcycle_native(self) -> None:
+        N, ops, comm = self._native, self.ops, self.comm
+        D, lib = ops.D, N["lib"]
+        n = len(self.levels)
+        hp = ctypes.byref(N["halo"]) if N["halo"] is not None else None
+        st = D.stream_ptr()
+        _lib.check(lib.gsb_slab_down(N["descs"], n, D.ptr(N["d_last"]), hp, self.halo, self.omega, self.pre, st),
+                   "gsb_slab_down")
+        d_full = comm.gather_rows(N["d_last"], self.gathered["rows_per_rank"], N["nzc"])
+        e_full = ops.coarse_vcycle(self.gathered, d_full, self.omega, self.pre, self.post, self.min_grid)
+        e_loc = e_full[N["lo"]:N["hi"]].contiguous()
+        N["e_keep"] = e_loc
+        _lib.check(lib.gsb_slab_up(N["descs"], n, D.ptr(e_loc), N["hi"] - N["lo"], N["roff_last"], hp, self.post + 1,
+                                   self.omega, self.post, st), "gsb_slab_up")
+
     def solve(self, source_owned, psi_bc_owned, *, tol: float = 1e-6, max_cycles: int = 500):
         """Returns (psi_owned_rows, residual_linf, n_cycles, converged) - residual/cycles/converged are
         global (identical on every rank), like multigrid_solve.py:352-463."""
@@ -447,6 +537,7 @@ class SlabMultigrid:
         if not st:
             st["f"], st["bc"], st["x"] = (ops.zeros((L.rows_loc, L.nr)) for _ in range(3))
             st["graph"] = None
+            st["native"] = self._native_setup(st["x"], st["f"])
         f, bc = st["f"], st["bc"]
         f.zero_()
         bc.zero_()
@@ -460,7 +551,10 @@ class SlabMultigrid:
         residual = comm.max(ops.residual_linf(L, x, f, r0, r1))
         cycles = 0
         def cycle(xc):
-            xc = self._vcycle(0, xc, f)
+            if st["native"]:
+                self._vcycle_native()  # works in place on the persistent level-0 buffers (xc is st["x"])
+            else:
+                xc = self._vcycle(0, xc, f)
             # Dirichlet ring (multigrid_solve.py:437-441,458)
             xc[own, 0] = bc[own, 0]
             xc[own, -1] = bc[own, -1]

@@ -43,7 +43,7 @@ if rank == 0:
     line = {"config": f"{n}x{n} multigrid_solve, slab decomposition", "n_gpus": world, "cycles": cyc, "residual": res,
             "converged": conv, "solve_ms": dt * 1e3, "ms_per_vcycle": dt * 1e3 / max(cyc, 1),
             "glups_per_vcycle": 8.0 * n_int * cyc / dt / 1e9, "levels_distributed": len(mgs.levels),
-            "cuda_graph": mgs.used_graph, "halo_transport": "nvlink-peer-kernels" if peer else "nccl-p2p", "halo_messages": comm.messages, "halo_mbytes": comm.bytes_sent / 1e6, "psi_sum": chk}
+            "cuda_graph": mgs.used_graph, "native_driver": bool(mgs._state.get("native")), "halo_transport": "nvlink-peer-kernels" if peer else "nccl-p2p", "halo_messages": comm.messages, "halo_mbytes": comm.bytes_sent / 1e6, "psi_sum": chk}
     if world == 1:
         rr, zz = np.meshgrid(R, Z)
         s = -np.exp(-((rr - 6.0) ** 2 + zz ** 2) / 0.5)
