@@ -689,31 +689,257 @@ def b_field(psi, RR, dr, dz):
     return -(1.0 / rs) * gz, (1.0 / rs) * gr
 
 
-def free_boundary_solve(prob: PicardProblem, positions, currents, turns, *, max_outer_iter=20,
-                        tol=1e-4) -> dict[str, Any]:
-    """fusion_kernel_free_boundary.py:623-739 without shape optimisation.
+def green_scalar(r_src, z_src, r_obs, z_obs) -> float:
+    """fusion_kernel_free_boundary.py:31-56 - scalar form (argument checks, self point -> 0)."""
+    if not np.all(np.isfinite([r_src, z_src, r_obs, z_obs])):
+        raise ValueError("Green's-function coordinates must be finite.")
+    if r_src <= 0.0 or r_obs <= 0.0:
+        raise ValueError("Green's-function radii must be positive.")
+    if (r_obs - r_src) ** 2 + (z_obs - z_src) ** 2 < 1e-24:
+        return 0.0
+    return float(green_vectorised(float(r_src), float(z_src), np.float64(r_obs), np.float64(z_obs)))
 
-    Outer loop: coil flux on the wall -> warm-started Picard -> max|dPsi| < tol.
+
+def interp_psi(psi, R, Z, dr, dz, r_pt, z_pt) -> float:
+    """fusion_kernel_free_boundary.py:562-581 - clamped bilinear sample of the flux map."""
+    nz, nr = psi.shape
+    ir = min(max(int(np.searchsorted(R, r_pt)) - 1, 0), nr - 2)
+    iz = min(max(int(np.searchsorted(Z, z_pt)) - 1, 0), nz - 2)
+    tr = min(max((r_pt - R[ir]) / dr, 0.0), 1.0)
+    tz = min(max((z_pt - Z[iz]) / dz, 0.0), 1.0)
+    return float((1 - tr) * (1 - tz) * psi[iz, ir] + tr * (1 - tz) * psi[iz, ir + 1]
+                 + (1 - tr) * tz * psi[iz + 1, ir] + tr * tz * psi[iz + 1, ir + 1])
+
+
+def sample_flux(psi, R, Z, dr, dz, points) -> np.ndarray:
+    """fusion_kernel_free_boundary.py:156-159."""
+    return np.array([interp_psi(psi, R, Z, dr, dz, float(r), float(z)) for r, z in np.asarray(points)], dtype=np.float64)
+
+
+def shape_target_flux(psi, R, Z, dr, dz, points, values=None) -> np.ndarray:
+    """fusion_kernel_free_boundary.py:584-605 - explicit values, else the mean sampled flux (isoflux)."""
+    pts = np.asarray(points, dtype=np.float64)
+    if pts.ndim != 2 or pts.shape[1] != 2 or pts.shape[0] == 0:
+        raise ValueError("target_flux_points must have shape (n_points, 2) with n_points > 0.")
+    if values is not None:
+        v = np.asarray(values, dtype=np.float64).reshape(-1)
+        if v.shape[0] != pts.shape[0]:
+            raise ValueError("target_flux_values must have the same length as target_flux_points.")
+        if not np.all(np.isfinite(v)):
+            raise ValueError("target_flux_values must contain finite values only.")
+        return v
+    return np.full(pts.shape[0], float(np.mean(sample_flux(psi, R, Z, dr, dz, pts))), dtype=np.float64)
+
+
+def _current_bounds(limits, n):
+    if limits is None:
+        return np.full(n, -np.inf), np.full(n, np.inf)
+    lim = np.asarray(limits, dtype=np.float64).reshape(-1)
+    if lim.shape[0] != n:
+        raise ValueError("current_limits must have one entry per coil.")
+    if not np.all(np.isfinite(lim)):
+        raise ValueError("current_limits must contain finite values only.")
+    return -np.abs(lim), np.abs(lim)
+
+
+def optimize_coil_currents(positions, turns, currents, points, target, *, limits=None, alpha=1e-4) -> np.ndarray:
+    """fusion_kernel_free_boundary.py:491-559 - bounded Tikhonov least squares [M^T; sqrt(a) I] I = [t; 0]
+    (scipy.optimize.lsq_linear, method trf - third-party, same call as the reference's)."""
+    from scipy.optimize import lsq_linear
+    M = mutual_matrix(positions, turns, points)
+    n = M.shape[0]
+    A = np.vstack([M.T, np.sqrt(alpha) * np.eye(n)])
+    b = np.concatenate([np.asarray(target, dtype=np.float64).reshape(-1), np.zeros(n)])
+    lb, ub = _current_bounds(limits, n)
+    res = lsq_linear(A, b, bounds=(lb, ub), method="trf")
+    if not bool(getattr(res, "success", False)) or not np.all(np.isfinite(res.x)):
+        return np.clip(np.asarray(currents, dtype=np.float64).copy(), lb, ub)
+    return np.asarray(res.x, dtype=np.float64)
+
+
+def points_inside_polygon(points, polygon) -> np.ndarray:
+    """fusion_kernel_free_boundary.py:113-134 - even-odd ray casting."""
+    pts, poly = np.asarray(points, dtype=np.float64), np.asarray(polygon, dtype=np.float64)
+    x, y = pts[:, 0], pts[:, 1]
+    inside = np.zeros(pts.shape[0], dtype=bool)
+    for i in range(poly.shape[0]):
+        xa, ya = poly[i]
+        xb, yb = poly[(i + 1) % poly.shape[0]]
+        inside ^= ((ya > y) != (yb > y)) & (x < (xb - xa) * (y - ya) / max(abs(yb - ya), 1.0e-300) + xa)
+    return inside
+
+
+def wall_contour(R, Z):
+    """fusion_kernel_free_boundary.py:608-620 - wall points counter-clockwise from (R_min, Z_min), and the
+    index arrays that read a (nz, nr) field in the same order (:716-723)."""
+    nr, nz = len(R), len(Z)
+    ir = np.concatenate([np.arange(nr), np.full(nz - 1, nr - 1), np.arange(nr - 2, -1, -1), np.zeros(nz - 2, dtype=int)])
+    iz = np.concatenate([np.zeros(nr, dtype=int), np.arange(1, nz), np.full(nr - 1, nz - 1), np.arange(nz - 2, 0, -1)])
+    return np.column_stack([np.asarray(R)[ir], np.asarray(Z)[iz]]), iz, ir
+
+
+def reconstruct_boundary_flux(positions, turns, currents, boundary_points, *, limiter_points=None, axis_point=None,
+                              x_points=None, target_flux=None) -> dict[str, Any]:
+    """fusion_kernel_free_boundary.py:162-267 - coil flux on a contour + limiter/axis/X-point diagnostics."""
+    obs = np.asarray(boundary_points, dtype=np.float64)
+    cur = np.asarray(currents, dtype=np.float64).reshape(-1)
+    resp = mutual_matrix(positions, turns, obs)
+    rec = resp.T @ cur
+    d: dict[str, Any] = {"boundary_points": obs, "reconstructed_flux": rec, "response_matrix": resp,
+                         "response_rank": int(np.linalg.matrix_rank(resp)), "point_count": int(obs.shape[0]),
+                         "coil_count": len(positions), "limiter_point_count": 0, "limiter_flux": np.array([]),
+                         "min_limiter_distance_m": None, "axis_point": None, "axis_flux": None, "x_point_count": 0,
+                         "x_point_flux": np.array([]), "x_point_flux_span": None, "x_point_pair_symmetry_abs_error": None}
+    if limiter_points is not None:
+        lim = np.asarray(limiter_points, dtype=np.float64)
+        frac = float(np.mean(points_inside_polygon(obs, lim)))
+        d.update(limiter_points=lim, limiter_flux=mutual_matrix(positions, turns, lim).T @ cur,
+                 limiter_point_count=int(lim.shape[0]),
+                 min_limiter_distance_m=float(np.min(np.linalg.norm(lim[:, None, :] - obs[None, :, :], axis=2))),
+                 boundary_containment_fraction=frac, boundary_containment_pass=bool(frac >= 1.0))
+    if axis_point is not None:
+        ax = np.asarray(axis_point, dtype=np.float64).reshape(1, 2)
+        d.update(axis_point=ax[0], axis_flux=float((mutual_matrix(positions, turns, ax).T @ cur)[0]))
+    if x_points is not None:
+        xo = np.asarray(x_points, dtype=np.float64)
+        xf = mutual_matrix(positions, turns, xo).T @ cur
+        sym = None
+        if d["axis_point"] is not None and xo.shape[0] == 2:
+            if abs(float(xo[0, 0] - xo[1, 0])) <= 1e-9 and abs(float(xo[0, 1] + xo[1, 1] - 2.0 * d["axis_point"][1])) <= 1e-9:
+                sym = float(abs(xf[0] - xf[1]))
+        d.update(x_points=xo, x_point_flux=xf, x_point_count=int(xo.shape[0]),
+                 x_point_flux_span=float(np.max(xf) - np.min(xf)) if xf.size else None,
+                 x_point_pair_symmetry_abs_error=sym)
+    if target_flux is not None:
+        t = np.asarray(target_flux, dtype=np.float64).reshape(-1)
+        r = rec - t
+        d.update(target_flux=t, residual=r, rmse=float(np.sqrt(np.mean(r ** 2))) if r.size else 0.0,
+                 max_abs_error=float(np.max(np.abs(r))) if r.size else 0.0)
+    return d
+
+
+def probe_response_matrix(positions, turns, *, flux_points=None, b_probe_points=None, b_probe_directions=None):
+    """fusion_kernel_free_boundary.py:282-367 - rows: flux loops (turns*G), then B probes as centred
+    differences of the same G: B_R = -(dG/dZ)/R, B_Z = (dG/dR)/R with eps_r = max(1e-5, 1e-5|R|),
+    eps_z = max(1e-5, 1e-5(1+|Z|)), R clamped to >= eps_r."""
+    fl = None if flux_points is None else np.asarray(flux_points, dtype=np.float64)
+    bp = None if b_probe_points is None else np.asarray(b_probe_points, dtype=np.float64)
+    if fl is None and bp is None:
+        raise ValueError("At least one flux point or B probe point must be provided.")
+    dirs = []
+    if bp is not None:
+        if b_probe_directions is None:
+            raise ValueError("b_probe_directions must be provided with b_probe_points.")
+        if len(b_probe_directions) != bp.shape[0]:
+            raise ValueError("b_probe_directions must have one entry per b_probe_point.")
+        dirs = [str(x).upper() for x in b_probe_directions]
+        if any(x not in ("R", "Z") for x in dirs):
+            raise ValueError("b_probe_directions entries must be 'R' or 'Z'.")
+    nf = 0 if fl is None else fl.shape[0]
+    nb = 0 if bp is None else bp.shape[0]
+    out = np.zeros((nf + nb, len(positions)))
+    for c, (rc, zc) in enumerate(positions):
+        t = turns[c] if c < len(turns) else 1
+        for i in range(nf):
+            out[i, c] = float(t) * green_scalar(rc, zc, fl[i, 0], fl[i, 1])
+        for i in range(nb):
+            r, z = float(bp[i, 0]), float(bp[i, 1])
+            er, ez = max(1e-5, 1e-5 * abs(r)), max(1e-5, 1e-5 * (1.0 + abs(z)))
+            rs = max(r, er)
+            if dirs[i] == "R":
+                hi, lo = float(t) * green_scalar(rc, zc, rs, z + ez), float(t) * green_scalar(rc, zc, rs, z - ez)
+                out[nf + i, c] = -(hi - lo) / (2.0 * ez * rs)
+            else:
+                hi, lo = float(t) * green_scalar(rc, zc, rs + er, z), float(t) * green_scalar(rc, zc, rs - er, z)
+                out[nf + i, c] = (hi - lo) / (2.0 * er * rs)
+    if not np.all(np.isfinite(out)):
+        raise ValueError("Magnetic probe response matrix contains non-finite entries.")
+    return out
+
+
+def reconstruct_currents_from_probes(response, target, prior, *, sigma=None, limits=None, alpha=1e-6) -> dict[str, Any]:
+    """fusion_kernel_free_boundary.py:370-488 - weighted Tikhonov fit around the prior currents, bounded."""
+    from scipy.optimize import lsq_linear
+    response, target = np.asarray(response, dtype=np.float64), np.asarray(target, dtype=np.float64).reshape(-1)
+    w = np.ones(response.shape[0])
+    if sigma is not None:
+        sg = np.asarray(sigma, dtype=np.float64).reshape(-1)
+        if np.any(sg <= 0.0):
+            raise ValueError("measurement_sigma must contain finite positive values only.")
+        w = 1.0 / sg
+    n = response.shape[1]
+    A, b = response * w[:, None], target * w
+    if alpha > 0.0:
+        A = np.vstack([A, np.sqrt(alpha) * np.eye(n)])
+        b = np.concatenate([b, np.sqrt(alpha) * np.asarray(prior, dtype=np.float64).reshape(-1)])
+    if limits is not None and np.any(np.asarray(limits) <= 0.0):
+        raise ValueError("current_limits must contain finite positive values only.")
+    lb, ub = _current_bounds(limits, n)
+    res = lsq_linear(A, b, bounds=(lb, ub), method="trf")
+    if not bool(getattr(res, "success", False)) or not np.all(np.isfinite(res.x)):
+        raise RuntimeError(f"Magnetic probe inverse reconstruction failed: {getattr(res, 'message', '')}")
+    cur = np.asarray(res.x, dtype=np.float64)
+    r = response @ cur - target
+    return {"coil_currents": cur, "residual": r, "weighted_residual": r * w,
+            "residual_rms": float(np.sqrt(np.mean(r ** 2))) if r.size else 0.0,
+            "weighted_residual_rms": float(np.sqrt(np.mean((r * w) ** 2))) if r.size else 0.0,
+            "response_rank": int(np.linalg.matrix_rank(response)),
+            "response_condition": float(np.linalg.cond(response)) if response.size else float("inf"),
+            "active_bounds": int(np.count_nonzero(np.isclose(cur, lb) | np.isclose(cur, ub)))}
+
+
+def free_boundary_solve(prob: PicardProblem, positions, currents, turns, *, max_outer_iter=20,
+                        tol=1e-4, optimize_shape=False, tikhonov_alpha=1e-4, target_points=None,
+                        target_values=None, current_limits=None, limiter_points=None, axis_point=None,
+                        x_points=None) -> dict[str, Any]:
+    """fusion_kernel_free_boundary.py:623-739.
+
+    Outer loop: coil flux on the wall -> warm-started Picard -> (optional) bounded re-fit of the coil
+    currents to the shape-control points -> max|dPsi| < tol; then the wall-contour reconstruction.
     """
     if max_outer_iter < 1:
         raise ValueError("max_outer_iter must be >= 1.")
     if not np.isfinite(tol) or tol < 0.0:
         raise ValueError("tol must be finite and >= 0.")
+    currents = np.asarray(currents, dtype=np.float64).copy()
     psi_ext = external_flux(prob.R, prob.Z, positions, currents, turns)
     diff = float("inf")
     outer = 0
     inner = []
+    shape = None
     for outer in range(max_outer_iter):
         copy_wall(prob.Psi, psi_ext)
         old = prob.Psi.copy()
         res = picard_solve(prob, preserve_initial_state=True, boundary_flux=psi_ext)
         inner.append(res["iterations"])
+        if optimize_shape and target_points is not None:
+            tgt = shape_target_flux(prob.Psi, prob.R, prob.Z, prob.dR, prob.dZ, target_points, target_values)
+            resp = mutual_matrix(positions, turns, target_points)
+            new = optimize_coil_currents(positions, turns, currents, target_points, tgt, limits=current_limits,
+                                         alpha=tikhonov_alpha)
+            ach = resp.T @ new
+            r = ach - tgt
+            rmse = float(np.sqrt(np.mean(r ** 2)))
+            active = 0
+            if current_limits is not None:
+                active = int(np.count_nonzero(np.isclose(np.abs(new), np.asarray(current_limits, dtype=np.float64), rtol=0.0)))
+            shape = {"solver_mode": "free_boundary_solver_shape_current_optimization",
+                     "target_point_count": int(tgt.shape[0]), "coil_count": len(positions),
+                     "response_rank": int(np.linalg.matrix_rank(resp.T)), "response_condition": float(np.linalg.cond(resp.T)),
+                     "flux_rmse": rmse, "flux_relative_rmse": rmse / max(float(np.sqrt(np.mean(tgt ** 2))), 1.0),
+                     "max_abs_flux_residual": float(np.max(np.abs(r))), "active_current_bounds": active,
+                     "target_flux": tgt.copy(), "achieved_flux": ach}
+            currents = new
+            psi_ext = external_flux(prob.R, prob.Z, positions, currents, turns)
         diff = float(np.max(np.abs(prob.Psi - old)))
         if diff < tol:
             break
-    return {"outer_iterations": outer + 1, "final_diff": diff,
-            "coil_currents": np.asarray(currents, dtype=np.float64).copy(),
-            "inner_iterations": inner, "psi": prob.Psi}
+    pts, iz, ir = wall_contour(prob.R, prob.Z)
+    recon = reconstruct_boundary_flux(positions, turns, currents, pts, limiter_points=limiter_points,
+                                      axis_point=axis_point, x_points=x_points, target_flux=psi_ext[iz, ir])
+    return {"outer_iterations": outer + 1, "final_diff": diff, "coil_currents": currents.copy(),
+            "vacuum_boundary_abs_error": recon["max_abs_error"], "boundary_reconstruction": recon,
+            "shape_optimization": shape, "inner_iterations": inner, "psi": prob.Psi}
 
 
 # --------------------------------------------------------------------------

@@ -7,8 +7,9 @@ meaning, result-dict keys and error behaviour.  Every numerical step runs in lib
 (``csrc/``); host code only marshals buffers.  A ``BatchedFusionKernel`` runs B independent
 equilibria (UQ / design sweeps) through the same kernels in one launch sequence.
 
-Out of scope here (SURVEY.md 8f): ``solver_method`` in {"newton", "anderson", "rust_multigrid"}
-and shape optimisation inside ``solve_free_boundary`` raise ``NotImplementedError``.
+The free-boundary layer (coil Green's functions, shape optimisation, probe reconstruction) lives in
+``free_boundary.py``.  Out of scope here: ``solver_method`` in {"newton", "anderson",
+"rust_multigrid"} raises ``NotImplementedError``.
 """
 from __future__ import annotations
 
@@ -25,6 +26,7 @@ import numpy as np
 
 from . import _device as D
 from . import _lib
+from .free_boundary import FreeBoundaryMixin
 _mg = __import__("importlib").import_module(__package__ + ".multigrid_solve")  # package re-exports a same-named function
 
 logger = logging.getLogger(__name__)
@@ -219,7 +221,7 @@ class _GridMixin:
         return out
 
 
-class FusionKernel(_GridMixin):
+class FusionKernel(FreeBoundaryMixin, _GridMixin):
     """Non-linear Grad-Shafranov equilibrium solver on one B200 (reference: fusion_kernel.py:104)."""
 
     def __init__(self, config_path, device: int | None = None) -> None:
@@ -436,47 +438,8 @@ class FusionKernel(_GridMixin):
             cs.x_point_flux_target = float(fb["x_point_flux_target"])
         return cs
 
-    def _compute_external_flux(self, coils: CoilSet) -> np.ndarray:
-        """fusion_kernel_free_boundary.py:83-93 (SI mu0, turns) on the device."""
-        w = [cur * (coils.turns[i] if i < len(coils.turns) else 1) for i, cur in enumerate(coils.currents)]
-        if not w:
-            return np.zeros((self.NZ, self.NR))
-        return self._coil_flux_dev(list(coils.positions), np.array([w]), 1)[0].cpu().numpy()
-
-    def _build_mutual_inductance_matrix(self, coils: CoilSet, obs_points) -> np.ndarray:
-        """fusion_kernel_free_boundary.py:137-153: M[coil, point]."""
-        lib = _lib.load()
-        obs = np.ascontiguousarray(np.asarray(obs_points, dtype=np.float64))
-        nc, npts = len(coils.positions), obs.shape[0]
-        rz = np.ascontiguousarray(np.asarray(coils.positions, dtype=np.float64).reshape(nc, 2))
-        turns = np.ascontiguousarray(
-            [coils.turns[k] if k < len(coils.turns) else 1 for k in range(nc)], dtype=np.int32)
-        m = D.empty((nc, npts), self.device)
-        _lib.check(lib.gsb_mutual_matrix(D.np_ptr(rz), turns.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), nc,
-                                         D.np_ptr(obs), npts, D.ptr(m), D.stream_ptr()), "gsb_mutual_matrix")
-        return m.cpu().numpy()
-
-    def solve_free_boundary(self, coils: CoilSet, max_outer_iter: int = 20, tol: float = 1e-4,
-                            optimize_shape: bool = False, tikhonov_alpha: float = 1e-4, **_ignored) -> dict[str, Any]:
-        """fusion_kernel_free_boundary.py:623-739: coil flux on the wall -> warm-started Picard."""
-        if max_outer_iter < 1:
-            raise ValueError("max_outer_iter must be >= 1.")
-        if not np.isfinite(tol) or tol < 0.0:
-            raise ValueError("tol must be finite and >= 0.")
-        if optimize_shape and coils.target_flux_points is not None:
-            raise NotImplementedError("shape optimisation is outside the B200 hot path (SURVEY.md 8f)")
-        psi_ext = self._compute_external_flux(coils)
-        diff = float("inf")
-        outer = 0
-        for outer in range(max_outer_iter):
-            self._apply_boundary_conditions(self.Psi, psi_ext)
-            psi_old = self.Psi.copy()
-            self.solve_equilibrium(preserve_initial_state=True, boundary_flux=psi_ext)
-            diff = float(np.max(np.abs(self.Psi - psi_old)))
-            if diff < tol:
-                break
-        return {"outer_iterations": outer + 1, "final_diff": diff, "coil_currents": np.asarray(coils.currents).copy(),
-                "shape_optimization": None}
+    # _compute_external_flux, _build_mutual_inductance_matrix, optimize_coil_currents, solve_free_boundary and the
+    # coil diagnostics come from FreeBoundaryMixin (free_boundary.py)
 
 
 def _picard_run(k: _GridMixin, params, psi0: np.ndarray, bc: np.ndarray, ip: np.ndarray, ped, *,

@@ -255,6 +255,87 @@ def gen_free_boundary():
     _save("free_boundary", **out)
 
 
+SHAPE_ALPHA = 1e-13  # currents are SI amperes (1e6-1e7): the default 1e-4 would regularise them to ~0
+
+
+def _shape_setup():
+    """Shared by the generator and by the tests (tests read the same arrays from the fixture)."""
+    th = np.linspace(0.0, 2.0 * np.pi, 9)[:-1] + 0.2
+    pts = np.column_stack([6.2 + 1.9 * np.cos(th), 3.1 * np.sin(th)])
+    limits = np.array([2.0e7, 6.0e6, 6.0e6, 6.0e6, 6.0e6, 2.0e7, 2.0e7])
+    return pts, limits
+
+
+def gen_free_boundary_shape():
+    """solve_free_boundary(optimize_shape=True) plus the coil-diagnostic functions built on the same
+    Green's function (fusion_kernel_free_boundary.py:156-739)."""
+    out = {}
+    cfg = _cfg("iter_validated_config.json", 33)
+    k = _kernel(cfg)
+    coils = k.build_coilset_from_config()
+    coils.currents = coils.currents * 1.0e6
+    pts, limits = _shape_setup()
+    coils.target_flux_points = pts
+    coils.current_limits = limits
+    out["currents0"], out["pts"], out["limits"] = coils.currents.copy(), pts, limits
+    # (i) isoflux target inferred from the solution, bounded currents
+    res = k.solve_free_boundary(coils, max_outer_iter=3, tol=1e-4, optimize_shape=True, tikhonov_alpha=SHAPE_ALPHA,
+                                limiter_points=np.array([[3.9, -4.6], [8.6, -4.6], [8.6, 4.6], [3.9, 4.6]]),
+                                axis_point=np.array([6.2, 0.0]), x_points=np.array([[5.0, -3.4], [5.0, 3.4]]))
+    so, br = res["shape_optimization"], res["boundary_reconstruction"]
+    out["psi"], out["currents"] = k.Psi.copy(), res["coil_currents"]
+    out["meta"] = np.array([res["outer_iterations"], res["final_diff"], res["vacuum_boundary_abs_error"]])
+    out["so_scalars"] = np.array([so["target_point_count"], so["coil_count"], so["response_rank"], so["response_condition"],
+                                  so["flux_rmse"], so["flux_relative_rmse"], so["max_abs_flux_residual"],
+                                  so["active_current_bounds"]], dtype=np.float64)
+    out["so_target"], out["so_achieved"] = so["target_flux"], so["achieved_flux"]
+    out["br_points"], out["br_flux"] = br["boundary_points"], br["reconstructed_flux"]
+    out["br_scalars"] = np.array([br["response_rank"], br["point_count"], br["coil_count"], br["limiter_point_count"],
+                                  br["min_limiter_distance_m"], br["boundary_containment_fraction"],
+                                  float(br["boundary_containment_pass"]), br["axis_flux"], br["x_point_count"],
+                                  br["x_point_flux_span"], br["x_point_pair_symmetry_abs_error"], br["rmse"],
+                                  br["max_abs_error"]], dtype=np.float64)
+    out["br_limiter_flux"], out["br_x_flux"] = br["limiter_flux"], br["x_point_flux"]
+    out["alpha"] = np.array(SHAPE_ALPHA)
+    print("  shape:", res["outer_iterations"], res["final_diff"], so["flux_rmse"], so["active_current_bounds"], res["coil_currents"])
+    # (ii) explicit target values, one outer iteration, unbounded
+    k2 = _kernel(cfg)
+    c2 = k2.build_coilset_from_config()
+    c2.currents = out["currents0"].copy()
+    c2.target_flux_points = pts
+    c2.target_flux_values = np.linspace(-0.4, 0.3, pts.shape[0])
+    r2 = k2.solve_free_boundary(c2, max_outer_iter=1, tol=0.0, optimize_shape=True, tikhonov_alpha=1e-6)
+    out["explicit_targets"], out["explicit_currents"] = c2.target_flux_values, r2["coil_currents"]
+    out["explicit_psi"] = k2.Psi.copy()
+    # (iii) interpolation and point sampling of the final flux map
+    sample = np.array([[2.0, -6.0], [10.0, 6.0], [6.123, 0.456], [9.99, -5.99], [1.0, 0.0], [12.0, 7.0], [4.25, 3.0]])
+    out["sample_pts"] = sample
+    out["sample_psi"] = ref_fb.sample_flux_at_points(k, sample)
+    # (iv) magnetic-probe response and bounded inverse reconstruction
+    c3 = k.build_coilset_from_config()
+    c3.currents = out["currents0"].copy()
+    c3.current_limits = limits
+    fl = np.array([[3.0, 0.0], [4.0, 3.5], [8.5, 2.0], [8.8, -1.5], [4.2, -3.6], [6.0, 4.4]])
+    bp = np.array([[3.2, 1.0], [3.2, -1.0], [8.9, 0.5], [6.5, 4.2], [6.5, -4.2], [0.0, 0.3]])
+    bd = ["R", "Z", "z", "r", "Z", "R"]
+    resp = ref_fb.build_magnetic_probe_response_matrix(k, c3, flux_points=fl, b_probe_points=bp, b_probe_directions=bd)
+    truth = out["currents0"] * np.array([1.1, 0.9, 1.0, 1.0, 1.2, 0.8, 1.05]) + np.array([0, 0, 2e5, -3e5, 0, 0, 0])
+    meas = resp @ truth
+    sigma = np.concatenate([np.full(len(fl), 1e-3), np.full(len(bp), 2e-3)])
+    rec = ref_fb.reconstruct_coil_currents_from_magnetic_probes(
+        k, c3, flux_points=fl, flux_measurements=meas[:len(fl)], b_probe_points=bp, b_probe_directions=bd,
+        b_probe_measurements=meas[len(fl):], measurement_sigma=sigma, tikhonov_alpha=1e-6)
+    out["probe_flux_pts"], out["probe_b_pts"], out["probe_dirs"] = fl, bp, np.array(bd)
+    out["probe_response"], out["probe_meas"], out["probe_sigma"] = resp, meas, sigma
+    out["probe_currents"], out["probe_residual"] = rec["coil_currents"], rec["residual"]
+    out["probe_scalars"] = np.array([rec["residual_rms"], rec["weighted_residual_rms"], rec["response_rank"],
+                                     rec["response_condition"], rec["active_bounds"]], dtype=np.float64)
+    out["green_scalar"] = np.array([ref_fb.green_function(6.2, 0.5, 4.0, -1.0), ref_fb.green_function(6.2, 0.5, 6.2, 0.5),
+                                    ref_fb.green_function(1.7, 0.0, 9.0, 5.0)])
+    out["cfg"] = np.array(json.dumps(cfg))
+    _save("free_boundary_shape", **out)
+
+
 # -- 7. the reference's compiled C++ solver (hpc/solver.cpp) ----------------------
 
 def gen_hpc():
@@ -298,7 +379,7 @@ def gen_elliptic():
 
 if __name__ == "__main__":
     which = sys.argv[1:] or ["ops", "mg_solve", "bench_smooth", "picard_pieces", "solves",
-                             "solve_129_validated", "free_boundary", "hpc", "elliptic"]
+                             "solve_129_validated", "free_boundary", "free_boundary_shape", "hpc", "elliptic"]
     for w in which:
         print("==", w)
         globals()["gen_" + w]()

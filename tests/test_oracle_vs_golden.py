@@ -207,6 +207,81 @@ def test_free_boundary_outer_loop():
     assert abs(r["final_diff"] - z["meta"][1]) <= 1e-12 * abs(z["meta"][1])
 
 
+def _shape_problem(z):
+    import json
+    cfg = json.loads(str(z["cfg"]))
+    return G.PicardProblem(cfg), [(c["r"], c["z"]) for c in cfg["coils"]]
+
+
+def test_free_boundary_shape_optimisation():
+    """solve_free_boundary(optimize_shape=True), bounded currents, isoflux target."""
+    z = golden("free_boundary_shape")
+    prob, pos = _shape_problem(z)
+    r = G.free_boundary_solve(prob, pos, z["currents0"], [1] * len(pos), max_outer_iter=3, tol=1e-4, optimize_shape=True,
+                              tikhonov_alpha=float(z["alpha"]), target_points=z["pts"], current_limits=z["limits"],
+                              limiter_points=np.array([[3.9, -4.6], [8.6, -4.6], [8.6, 4.6], [3.9, 4.6]]),
+                              axis_point=np.array([6.2, 0.0]), x_points=np.array([[5.0, -3.4], [5.0, 3.4]]))
+    assert r["outer_iterations"] == int(z["meta"][0])
+    assert rel_l2(r["psi"], z["psi"]) <= 1e-12
+    np.testing.assert_allclose(r["coil_currents"], z["currents"], rtol=1e-10, atol=0)
+    assert abs(r["final_diff"] - z["meta"][1]) <= 1e-9 * abs(z["meta"][1])
+    so, sc = r["shape_optimization"], z["so_scalars"]
+    assert (so["target_point_count"], so["coil_count"], so["response_rank"], so["active_current_bounds"]) == \
+        (int(sc[0]), int(sc[1]), int(sc[2]), int(sc[7]))
+    np.testing.assert_allclose([so["response_condition"], so["flux_rmse"], so["flux_relative_rmse"], so["max_abs_flux_residual"]],
+                               sc[3:7], rtol=1e-9)
+    np.testing.assert_allclose(so["target_flux"], z["so_target"], rtol=1e-11)
+    np.testing.assert_allclose(so["achieved_flux"], z["so_achieved"], rtol=1e-9, atol=1e-12)
+    br, bs = r["boundary_reconstruction"], z["br_scalars"]
+    np.testing.assert_array_equal(br["boundary_points"], z["br_points"])
+    np.testing.assert_allclose(br["reconstructed_flux"], z["br_flux"], rtol=1e-10, atol=1e-13)
+    assert (br["response_rank"], br["point_count"], br["coil_count"], br["limiter_point_count"], br["x_point_count"]) == \
+        (int(bs[0]), int(bs[1]), int(bs[2]), int(bs[3]), int(bs[8]))
+    assert br["min_limiter_distance_m"] == bs[4] and br["boundary_containment_fraction"] == bs[5]
+    assert float(br["boundary_containment_pass"]) == bs[6]
+    np.testing.assert_allclose([br["axis_flux"], br["x_point_flux_span"], br["x_point_pair_symmetry_abs_error"]],
+                               [bs[7], bs[9], bs[10]], rtol=1e-9, atol=1e-13)
+    assert br["max_abs_error"] <= 1e-9 and abs(r["vacuum_boundary_abs_error"] - z["meta"][2]) <= 1e-9
+    np.testing.assert_allclose(br["limiter_flux"], z["br_limiter_flux"], rtol=1e-10)
+    np.testing.assert_allclose(br["x_point_flux"], z["br_x_flux"], rtol=1e-10)
+    # interpolation of the final flux map, incl. points outside the box (clamped)
+    np.testing.assert_allclose(G.sample_flux(prob.Psi, prob.R, prob.Z, prob.dR, prob.dZ, z["sample_pts"]), z["sample_psi"],
+                               rtol=1e-11, atol=1e-13)
+
+
+def test_free_boundary_explicit_targets_unbounded():
+    z = golden("free_boundary_shape")
+    prob, pos = _shape_problem(z)
+    r = G.free_boundary_solve(prob, pos, z["currents0"], [1] * len(pos), max_outer_iter=1, tol=0.0, optimize_shape=True,
+                              tikhonov_alpha=1e-6, target_points=z["pts"], target_values=z["explicit_targets"])
+    assert rel_l2(r["psi"], z["explicit_psi"]) <= 1e-13
+    np.testing.assert_allclose(r["coil_currents"], z["explicit_currents"], rtol=1e-9, atol=0)
+    with pytest.raises(ValueError):
+        G.shape_target_flux(prob.Psi, prob.R, prob.Z, prob.dR, prob.dZ, z["pts"], z["explicit_targets"][:-1])
+
+
+def test_magnetic_probe_response_and_reconstruction():
+    z = golden("free_boundary_shape")
+    _, pos = _shape_problem(z)
+    resp = G.probe_response_matrix(pos, [1] * len(pos), flux_points=z["probe_flux_pts"], b_probe_points=z["probe_b_pts"],
+                                   b_probe_directions=[str(d) for d in z["probe_dirs"]])
+    np.testing.assert_array_equal(resp, z["probe_response"])
+    rec = G.reconstruct_currents_from_probes(resp, z["probe_meas"], z["currents0"], sigma=z["probe_sigma"],
+                                             limits=z["limits"], alpha=1e-6)
+    np.testing.assert_allclose(rec["coil_currents"], z["probe_currents"], rtol=1e-10, atol=1e-6)
+    np.testing.assert_allclose(rec["residual"], z["probe_residual"], rtol=1e-6, atol=1e-12)
+    ps = z["probe_scalars"]
+    assert (rec["response_rank"], rec["active_bounds"]) == (int(ps[2]), int(ps[4]))
+    np.testing.assert_allclose([rec["residual_rms"], rec["weighted_residual_rms"], rec["response_condition"]],
+                               [ps[0], ps[1], ps[3]], rtol=1e-6)
+    np.testing.assert_array_equal([G.green_scalar(6.2, 0.5, 4.0, -1.0), G.green_scalar(6.2, 0.5, 6.2, 0.5),
+                                   G.green_scalar(1.7, 0.0, 9.0, 5.0)], z["green_scalar"])
+    with pytest.raises(ValueError):
+        G.green_scalar(0.0, 0.0, 1.0, 1.0)
+    with pytest.raises(ValueError):
+        G.probe_response_matrix(pos, [1] * len(pos), b_probe_points=z["probe_b_pts"], b_probe_directions=["R", "Q", "R", "R", "R", "R"])
+
+
 def test_hpc_cpp_arithmetic():
     """oracle.hpc_run_step vs the compiled reference solver.cpp (FMA contraction allowed there)."""
     z = golden("hpc_solver")
