@@ -942,6 +942,47 @@ def free_boundary_solve(prob: PicardProblem, positions, currents, turns, *, max_
             "shape_optimization": shape, "inner_iterations": inner, "psi": prob.Psi}
 
 
+def is_boundary_xpoint(r_x, z_x, r_min, r_max, z_min, z_max, margin_fraction=0.01) -> bool:
+    """tools/parallel_gen_iter.py:50-69 - X-point within 1 % of the box edge = clipped equilibrium."""
+    mr = max((r_max - r_min) * margin_fraction, 1.0e-12)
+    mz = max((z_max - z_min) * margin_fraction, 1.0e-12)
+    return bool(r_x <= r_min + mr or r_x >= r_max - mr or z_x <= z_min + mz or z_x >= z_max - mz)
+
+
+def dataset_chunk(cfg: dict[str, Any], n_samples: int, seed: int, allow_boundary_xpoints: bool):
+    """tools/parallel_gen_iter.py:72-141 - one worker's chunk: per sample, every coil current x U(0.85,1.15)
+    and Ip x U(0.8,1.2) (drawn in that order from default_rng(seed)), a cold-started solve, then the 12
+    features [Ip/1e6, 5.3, R_ax, Z_ax, 1, 1, psi_ax, psi_x, 1.7, 0.33, 0.33, 3.0] and the flattened psi."""
+    import copy
+    cfg = copy.deepcopy(cfg)
+    base_i = [float(c["current"]) for c in cfg["coils"]]
+    base_ip = float(cfg["physics"]["plasma_current_target"])
+    rng = np.random.default_rng(seed)
+    X, Y, rejected, failed = [], [], 0, 0
+    for _ in range(n_samples):
+        for i, c in enumerate(cfg["coils"]):
+            c["current"] = base_i[i] * rng.uniform(0.85, 1.15)
+        ip = base_ip * rng.uniform(0.8, 1.2)
+        cfg["physics"]["plasma_current_target"] = ip
+        prob = PicardProblem(cfg)
+        try:
+            picard_solve(prob)
+        except Exception:
+            failed += 1
+            continue
+        iz, ir, pax = find_axis(prob.Psi)
+        saddle = bool(cfg["solver"].get("xpoint_use_saddle_detection", False))
+        (rx, zx), px = find_x_point(prob.Psi, prob.R, prob.Z, prob.dR, prob.dZ, cfg["dimensions"]["Z_min"], saddle=saddle)
+        if not allow_boundary_xpoints and is_boundary_xpoint(float(rx), float(zx), float(prob.R.min()), float(prob.R.max()),
+                                                             float(prob.Z.min()), float(prob.Z.max())):
+            rejected += 1
+            continue
+        X.append([float(ip / 1e6), 5.3, float(prob.R[ir]), float(prob.Z[iz]), 1.0, 1.0, float(pax), float(px),
+                  1.7, 0.33, 0.33, 3.0])
+        Y.append(prob.Psi.ravel().copy())
+    return np.asarray(X, dtype=np.float64), np.asarray(Y, dtype=np.float64), rejected, failed
+
+
 # --------------------------------------------------------------------------
 # the reference's C ABI arithmetic (src/scpn_fusion/hpc/solver.cpp)
 # --------------------------------------------------------------------------

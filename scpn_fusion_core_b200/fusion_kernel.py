@@ -583,6 +583,17 @@ class BatchedFusionKernel(_GridMixin):
             res["gs_residual_history"] = dev["gs_hist"].cpu().numpy()
         return res
 
+    def topology(self, psi_dev) -> np.ndarray:
+        """O-/X-point of each flux map of a device batch (a10, a11): host (B, 8) rows
+        [iz_ax, ir_ax, psi_ax, iz_x, ir_x, psi_x, found_x, min psi] (gsb_topology)."""
+        B = int(psi_dev.shape[0])
+        ctx = self._context(B)
+        out = D.empty((B, 8), self.device)
+        saddle = 1 if bool(self.cfg.get("solver", {}).get("xpoint_use_saddle_detection", False)) else 0
+        _lib.check(ctx.lib.gsb_topology(ctx.handle, D.ptr(psi_dev), B, float(self.cfg["dimensions"]["Z_min"]), saddle,
+                                        D.ptr(out), D.stream_ptr()), "gsb_topology")
+        return out.cpu().numpy()
+
     def unpack_summary(self, s: np.ndarray) -> dict[str, Any]:
         """Decode the [B,16] summary rows of gsb_picard_solve (include/gsb200.h)."""
         return {

@@ -336,6 +336,33 @@ def gen_free_boundary_shape():
     _save("free_boundary_shape", **out)
 
 
+def gen_dataset():
+    """tools/parallel_gen_iter.py::generate_chunk - the reference's UQ/dataset producer (SURVEY.md 8f row 3)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_parallel_gen_iter", os.path.join(REF, "tools", "parallel_gen_iter.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    out = {}
+    cases = [("val65", "iter_validated_config.json", 65, 2, 42, False), ("val", "iter_validated_config.json", 33, 3, 42, True),
+             ("iter", "iter_config.json", 33, 2, 43, False), ("iter_allow", "iter_config.json", 33, 2, 43, True)]
+    for tag, name, grid, n, seed, allow in cases:
+        cfg = _cfg(name, grid)
+        fd, path = tempfile.mkstemp(suffix=".json")
+        with os.fdopen(fd, "w") as f:
+            json.dump(cfg, f)
+        X, Y, rej, failed = mod.generate_chunk(n, path, seed, allow)
+        os.unlink(path)
+        out[tag + "_cfg"] = np.array(json.dumps(cfg))
+        out[tag + "_X"], out[tag + "_Y"] = X, Y
+        out[tag + "_meta"] = np.array([n, seed, int(allow), rej, failed])
+        print(f"  {tag}: X{X.shape} Y{Y.shape} rejected={rej} failed={failed}")
+    out["boundary_checks"] = np.array([mod.is_boundary_xpoint(2.05, 0.0, 2.0, 10.0, -6.0, 6.0),
+                                       mod.is_boundary_xpoint(2.09, 0.0, 2.0, 10.0, -6.0, 6.0),
+                                       mod.is_boundary_xpoint(5.0, -5.87, 2.0, 10.0, -6.0, 6.0),
+                                       mod.is_boundary_xpoint(5.0, -5.89, 2.0, 10.0, -6.0, 6.0)])
+    _save("dataset", **out)
+
+
 # -- 7. the reference's compiled C++ solver (hpc/solver.cpp) ----------------------
 
 def gen_hpc():
@@ -379,7 +406,7 @@ def gen_elliptic():
 
 if __name__ == "__main__":
     which = sys.argv[1:] or ["ops", "mg_solve", "bench_smooth", "picard_pieces", "solves",
-                             "solve_129_validated", "free_boundary", "free_boundary_shape", "hpc", "elliptic"]
+                             "solve_129_validated", "free_boundary", "free_boundary_shape", "dataset", "hpc", "elliptic"]
     for w in which:
         print("==", w)
         globals()["gen_" + w]()
