@@ -6,7 +6,7 @@ A drop-in for the equilibrium entry points of anulum/scpn-fusion-core
 behind a C ABI (``include/gsb200.h``).  See DESIGN.md / INTEGRATION.md.
 """
 from . import _lib  # noqa: F401
-from . import dataset, free_boundary  # noqa: F401
+from . import dataset, eqdsk, free_boundary  # noqa: F401
 from .fusion_kernel import (  # noqa: F401
     BatchedFusionKernel, CoilSet, FusionKernel, shard_range, solve_sharded, validate_config,
 )

@@ -363,6 +363,105 @@ def gen_dataset():
     _save("dataset", **out)
 
 
+def _fortran_body(values, width=16, prec=9, dexp=False):
+    """Fixed-width Fortran (5e16.9) text with NO separating blanks: negative values run into their neighbours."""
+    cells = []
+    for v in values:
+        c = f"{v:{width}.{prec}E}"
+        cells.append(c.replace("E", "D") if dexp else c)
+    return "".join("".join(cells[i:i + 5]).lstrip() + "\n" for i in range(0, len(cells), 5))
+
+
+def gen_eqdsk():
+    """core/eqdsk.py: writer bytes, reader values (free-format, run-together fixed-width, D exponents),
+    to_config(), the public-SPARC adapter and the rejected inputs."""
+    from scpn_fusion.core import eqdsk as ref_eq
+    out = {}
+    rng = np.random.default_rng(77)
+    nw, nh, nb, nl = 9, 7, 7, 5
+    eq = ref_eq.GEqdsk(description="synthetic case for the B200 reader/writer parity test, long description", nw=nw, nh=nh,
+                       rdim=2.5, zdim=4.0, rcentr=1.85, rleft=0.6, zmid=0.1, rmaxis=1.9, zmaxis=0.05, simag=-0.42,
+                       sibry=0.13, bcentr=-12.2, current=8.7e6, fpol=rng.normal(size=nw), pres=rng.uniform(0, 1e5, nw),
+                       ffprime=rng.normal(size=nw), pprime=rng.normal(size=nw) * 1e3, qpsi=rng.uniform(1, 5, nw),
+                       psirz=rng.normal(size=(nh, nw)), rbdry=rng.uniform(1, 2.5, nb), zbdry=rng.uniform(-1, 1, nb),
+                       rlim=rng.uniform(0.7, 3.0, nl), zlim=rng.uniform(-1.9, 2.0, nl))
+    tmp = tempfile.mkdtemp()
+    pa = os.path.join(tmp, "a.geqdsk")
+    ref_eq.write_geqdsk(eq, pa)
+    out["a_bytes"] = np.frombuffer(open(pa, "rb").read(), dtype=np.uint8)
+    back = ref_eq.read_geqdsk(pa)
+    for n in ("fpol", "pres", "ffprime", "pprime", "qpsi", "psirz", "rbdry", "zbdry", "rlim", "zlim"):
+        out["a_" + n] = getattr(back, n)
+        np.testing.assert_array_equal(getattr(back, n), getattr(eq, n))  # 17 significant digits round-trip
+    out["a_scalars"] = np.array([getattr(back, n) for n in ("rdim", "zdim", "rcentr", "rleft", "zmid", "rmaxis", "zmaxis",
+                                                             "simag", "sibry", "bcentr", "current")])
+    out["a_desc"] = np.array(back.description)
+    out["a_config"] = np.array(json.dumps(back.to_config("case_a")))
+    out["a_r"], out["a_z"] = back.r, back.z
+    out["a_psin"] = back.psi_to_norm(back.psirz)
+    # no contours at all, and an odd pair count (line-break rule of the writer)
+    for tag, nb2, nl2 in (("b", 0, 0), ("c", 3, 1)):
+        e2 = ref_eq.GEqdsk(**{**eq.__dict__, "rbdry": eq.rbdry[:nb2], "zbdry": eq.zbdry[:nb2], "rlim": eq.rlim[:nl2],
+                              "zlim": eq.zlim[:nl2], "description": "short"})
+        p2 = os.path.join(tmp, tag + ".geqdsk")
+        ref_eq.write_geqdsk(e2, p2)
+        out[tag + "_bytes"] = np.frombuffer(open(p2, "rb").read(), dtype=np.uint8)
+        out[tag + "_config"] = np.array(json.dumps(ref_eq.read_geqdsk(p2).to_config()))
+    # fixed-width body without blanks (+ D exponents), as legacy EFIT writers produce
+    scal = [2.5, 4.0, 1.85, 0.6, -0.1, 1.9, -0.05, -0.42, 0.13, -12.2, -8.7e6, -0.42, 0.0, 1.9, 0.0, -0.05, 0.0, 0.13, 0.0, 0.0]
+    vals = np.concatenate([eq.fpol, eq.pres, -np.abs(eq.ffprime), eq.pprime, -np.abs(eq.psirz).ravel(), eq.qpsi])
+    for tag, dexp in (("f", False), ("d", True)):
+        text = f"  EFITD    01/01/2026    #123456  1000ms           3 {nw} {nh}\n" + _fortran_body(scal, dexp=dexp) \
+            + _fortran_body(vals, dexp=dexp) + f"{nb:5d}{nl:5d}\n" \
+            + _fortran_body(np.column_stack([eq.rbdry, -np.abs(eq.zbdry)]).ravel(), dexp=dexp) \
+            + _fortran_body(np.column_stack([eq.rlim, eq.zlim]).ravel(), dexp=dexp)
+        pf = os.path.join(tmp, tag + ".geqdsk")
+        open(pf, "w").write(text)
+        e = ref_eq.read_geqdsk(pf)
+        out[tag + "_bytes"] = np.frombuffer(text.encode(), dtype=np.uint8)
+        out[tag + "_desc"] = np.array(e.description)
+        out[tag + "_scalars"] = np.array([getattr(e, n) for n in ("rdim", "zdim", "rcentr", "rleft", "zmid", "rmaxis", "zmaxis",
+                                                                   "simag", "sibry", "bcentr", "current")])
+        for n in ("fpol", "pres", "ffprime", "pprime", "qpsi", "psirz", "rbdry", "zbdry", "rlim", "zlim"):
+            out[tag + "_" + n] = getattr(e, n)
+    # public SPARC named adapter
+    ps = os.path.join(tmp, "sparc_1305.eqdsk")
+    ref_eq.write_geqdsk(eq, ps)
+    e = ref_eq.read_geqdsk(ps, source_convention_mode="public_sparc_named_adapter")
+    out["sparc_ffprime"], out["sparc_pprime"] = e.ffprime, e.pprime
+    out["sparc_meta"] = np.array(json.dumps({"convention": e.source_convention, "adapter": e.source_convention_adapter,
+                                             "ok": e.source_convention_adapter_pass, "meta": e.source_convention_metadata}))
+    e = ref_eq.read_geqdsk(pa, source_convention_mode="public_sparc_named_adapter")
+    out["nomatch_meta"] = np.array(json.dumps({"convention": e.source_convention, "adapter": e.source_convention_adapter,
+                                               "ok": e.source_convention_adapter_pass, "meta": e.source_convention_metadata}))
+    # inputs the reference rejects with ValueError
+    good = open(pa).read()
+    lines = good.splitlines(keepends=True)
+    bad = {"empty": "", "short_header": "x 9\n", "tiny_grid": lines[0][:-10] + "    1    7\n" + "".join(lines[1:]),
+           "truncated": "".join(lines[:12]), "nan_token": good.replace(lines[3][:24], "                     nan", 1),
+           "huge_grid": lines[0][:-10] + " 2000 2000\n" + "".join(lines[1:]),
+           "neg_count": good.replace(f"{nb:5d}{nl:5d}\n", f"{-1:5d}{nl:5d}\n"),
+           "equal_psi": None}
+    e3 = ref_eq.GEqdsk(**{**eq.__dict__, "sibry": eq.simag})
+    p3 = os.path.join(tmp, "eq.geqdsk")
+    ref_eq.write_geqdsk(e3, p3)
+    bad["equal_psi"] = open(p3).read()
+    names = []
+    for k, text in bad.items():
+        pb = os.path.join(tmp, "bad_" + k)
+        open(pb, "w").write(text)
+        try:
+            ref_eq.read_geqdsk(pb)
+        except ValueError as exc:
+            names.append(k)
+            out["bad_" + k] = np.frombuffer(text.encode(), dtype=np.uint8)
+            print("   rejects", k, "->", str(exc)[:60])
+        else:
+            print("   ACCEPTS", k)
+    out["bad_names"] = np.array(names)
+    _save("eqdsk", **out)
+
+
 # -- 7. the reference's compiled C++ solver (hpc/solver.cpp) ----------------------
 
 def gen_hpc():
@@ -406,7 +505,7 @@ def gen_elliptic():
 
 if __name__ == "__main__":
     which = sys.argv[1:] or ["ops", "mg_solve", "bench_smooth", "picard_pieces", "solves",
-                             "solve_129_validated", "free_boundary", "free_boundary_shape", "dataset", "hpc", "elliptic"]
+                             "solve_129_validated", "free_boundary", "free_boundary_shape", "dataset", "eqdsk", "hpc", "elliptic"]
     for w in which:
         print("==", w)
         globals()["gen_" + w]()

@@ -1,0 +1,137 @@
+"""G-EQDSK reader/writer (reference core/eqdsk.py) against tests/golden/eqdsk.npz, which
+holds files written and values parsed by the UNMODIFIED reference: byte-identical writer output, exact parsed
+values for free-format / run-together fixed-width / D-exponent inputs, identical to_config() dictionaries,
+the public-SPARC adapter and the inputs the reference rejects."""
+from __future__ import annotations
+
+import json
+
+import numpy as np
+import pytest
+
+from conftest import golden
+
+ARRAYS = ("fpol", "pres", "ffprime", "pprime", "qpsi", "psirz", "rbdry", "zbdry", "rlim", "zlim")
+SCALARS = ("rdim", "zdim", "rcentr", "rleft", "zmid", "rmaxis", "zmaxis", "simag", "sibry", "bcentr", "current")
+
+
+def _put(tmp_path, name, data) -> str:
+    p = tmp_path / name
+    p.write_bytes(bytes(np.asarray(data, dtype=np.uint8)))
+    return str(p)
+
+
+def test_read_write_roundtrip_is_byte_identical(tmp_path):
+    from scpn_fusion_core_b200 import eqdsk
+    z = golden("eqdsk")
+    for tag in ("a", "b", "c"):
+        eq = eqdsk.read_geqdsk(_put(tmp_path, tag + ".geqdsk", z[tag + "_bytes"]))
+        out = tmp_path / (tag + "_out.geqdsk")
+        eqdsk.write_geqdsk(eq, out)
+        assert out.read_bytes() == bytes(z[tag + "_bytes"]), tag
+    eq = eqdsk.read_geqdsk(_put(tmp_path, "a.geqdsk", z["a_bytes"]))
+    for n in ARRAYS:
+        np.testing.assert_array_equal(getattr(eq, n), z["a_" + n])
+    np.testing.assert_array_equal([getattr(eq, n) for n in SCALARS], z["a_scalars"])
+    assert eq.description == str(z["a_desc"]) and (eq.nw, eq.nh) == (9, 7)
+    np.testing.assert_array_equal(eq.r, z["a_r"])
+    np.testing.assert_array_equal(eq.z, z["a_z"])
+    np.testing.assert_array_equal(eq.psi_to_norm(eq.psirz), z["a_psin"])
+    np.testing.assert_array_equal(eq.psi_norm, np.linspace(0.0, 1.0, 9))
+
+
+def test_to_config_matches_reference(tmp_path):
+    from scpn_fusion_core_b200 import eqdsk
+    z = golden("eqdsk")
+    assert eqdsk.read_geqdsk(_put(tmp_path, "a", z["a_bytes"])).to_config("case_a") == json.loads(str(z["a_config"]))
+    for tag in ("b", "c"):
+        assert eqdsk.read_geqdsk(_put(tmp_path, tag, z[tag + "_bytes"])).to_config() == json.loads(str(z[tag + "_config"]))
+    cfg = eqdsk.read_geqdsk(_put(tmp_path, "a", z["a_bytes"])).to_config()
+    from scpn_fusion_core_b200 import validate_config
+    cfg["coils"] = [{"r": 3.0, "z": 0.0, "current": 1.0}]
+    validate_config(cfg)  # the dictionary is a loadable FusionKernel config
+
+
+def test_fixed_width_run_together_and_d_exponents(tmp_path):
+    from scpn_fusion_core_b200 import eqdsk
+    z = golden("eqdsk")
+    for tag in ("f", "d"):
+        eq = eqdsk.read_geqdsk(_put(tmp_path, tag, z[tag + "_bytes"]))
+        assert eq.description == str(z[tag + "_desc"])
+        np.testing.assert_array_equal([getattr(eq, n) for n in SCALARS], z[tag + "_scalars"])
+        for n in ARRAYS:
+            np.testing.assert_array_equal(getattr(eq, n), z[tag + "_" + n])
+
+
+def test_public_sparc_adapter(tmp_path):
+    from scpn_fusion_core_b200 import eqdsk
+    z = golden("eqdsk")
+
+    def meta(e):
+        return {"convention": e.source_convention, "adapter": e.source_convention_adapter,
+                "ok": e.source_convention_adapter_pass, "meta": e.source_convention_metadata}
+    e = eqdsk.read_geqdsk(_put(tmp_path, "sparc_1305.eqdsk", z["a_bytes"]), source_convention_mode="public_sparc_named_adapter")
+    np.testing.assert_array_equal(e.ffprime, z["sparc_ffprime"])
+    np.testing.assert_array_equal(e.pprime, z["sparc_pprime"])
+    assert meta(e) == json.loads(str(z["sparc_meta"]))
+    e = eqdsk.read_geqdsk(_put(tmp_path, "a.geqdsk", z["a_bytes"]), source_convention_mode="public_sparc_named_adapter")
+    assert meta(e) == json.loads(str(z["nomatch_meta"]))
+    np.testing.assert_array_equal(e.ffprime, z["a_ffprime"])
+    e = eqdsk.read_geqdsk(_put(tmp_path, "sparc_1305.eqdsk", z["a_bytes"]))  # default mode never rescales
+    np.testing.assert_array_equal(e.ffprime, z["a_ffprime"])
+    with pytest.raises(ValueError):
+        eqdsk.read_geqdsk(_put(tmp_path, "x", z["a_bytes"]), source_convention_mode="guess")
+
+
+def test_rejected_inputs(tmp_path):
+    from scpn_fusion_core_b200 import eqdsk
+    z = golden("eqdsk")
+    names = [str(n) for n in z["bad_names"]]
+    assert {"empty", "short_header", "tiny_grid", "truncated", "huge_grid", "neg_count", "equal_psi"} <= set(names)
+    for n in names:
+        with pytest.raises(ValueError):
+            eqdsk.read_geqdsk(_put(tmp_path, "bad_" + n, z["bad_" + n]))
+    eq = eqdsk.read_geqdsk(_put(tmp_path, "a", z["a_bytes"]))
+    eq.rbdry = eq.rbdry[:-1]
+    with pytest.raises(ValueError):
+        eq.to_config()
+    with pytest.raises(ValueError):
+        eqdsk.validate_geqdsk(eq)
+    big = tmp_path / "big"
+    big.write_bytes(b" " * (eqdsk.MAX_GEQDSK_BYTES + 1))
+    with pytest.raises(ValueError):
+        eqdsk.read_geqdsk(big)
+
+
+class _SolvedStub:
+    """A FusionKernel look-alike (host arrays only) for from_kernel()."""
+
+    def __init__(self):
+        self.NR, self.NZ = 9, 7
+        self.R, self.Z = np.linspace(1.0, 3.0, 9), np.linspace(-1.5, 1.5, 7)
+        rr, zz = np.meshgrid(self.R, self.Z)
+        self.Psi = np.exp(-((rr - 2.0) ** 2 + zz ** 2))
+        self.cfg = {"physics": {"plasma_current_target": 8.7}}
+
+    def _find_magnetic_axis(self):
+        iz, ir = np.unravel_index(int(np.argmax(self.Psi)), self.Psi.shape)
+        return int(iz), int(ir), float(self.Psi[iz, ir])
+
+    def find_x_point(self, psi):
+        return (1.5, -1.0), 0.25
+
+
+def test_from_kernel_roundtrip(tmp_path):
+    from scpn_fusion_core_b200 import eqdsk
+    k = _SolvedStub()
+    eq = eqdsk.from_kernel(k, boundary=[[1.5, 0.0], [2.5, 0.0], [2.0, 1.0]])
+    assert (eq.rmaxis, eq.zmaxis, eq.simag, eq.sibry, eq.current) == (2.0, 0.0, 1.0, 0.25, 8.7e6)
+    p = tmp_path / "k.geqdsk"
+    eqdsk.write_geqdsk(eq, p)
+    back = eqdsk.read_geqdsk(p)
+    np.testing.assert_array_equal(back.psirz, k.Psi)
+    np.testing.assert_array_equal(back.r, k.R)
+    np.testing.assert_allclose(back.z, k.Z, rtol=0, atol=1e-15)
+    cfg = back.to_config("again")
+    assert cfg["grid_resolution"] == [9, 7] and cfg["physics"]["plasma_current_target"] == 8.7
+    assert len(cfg["free_boundary"]["target_flux_points"]) == 3
