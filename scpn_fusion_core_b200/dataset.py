@@ -6,7 +6,8 @@ runs ``FusionKernel.solve_equilibrium()`` and keeps 12 features + the flattened 
 X-point sits on the box edge (``parallel_gen_iter.py:72-141``).  Here one chunk is ONE batched device
 solve (``BatchedFusionKernel``) followed by one batched topology launch on the final flux maps; the
 random draws are made in the reference's order, so chunk ``i`` reproduces worker ``i``'s samples and
-the ``--workers`` value only decides how the seeds partition the request.  Under torchrun the chunks
+the ``--workers`` value only decides how the seeds partition the request (all chunks of a rank share one
+batched solve).  Under torchrun the chunks
 are dealt round-robin to the ranks (independent units, no data-path collective) and rank 0 writes the
 same ``.npz`` (X, Y) and ``.report.json`` the reference writes.
 
@@ -57,43 +58,65 @@ def draw_perturbations(cfg: dict, n_samples: int, seed: int) -> tuple[np.ndarray
     return cc, ip
 
 
-def generate_chunk(n_samples: int, config_path, seed: int, allow_boundary_xpoints: bool, *, device: int | None = None):
-    """One worker's chunk -> ``(X (n_valid, 12), Y (n_valid, nz*nr), rejected_boundary_xpoints, failed_solves)``.
+MAX_BATCH = 8192  # equilibria per device solve (129^2: ~1.1 GB per field)
 
-    ``config_path``: path or config dict.  A sample whose solve diverges counts as failed when the config
-    sets ``solver.fail_on_diverge`` (the reference's solve raises there, :103,138-140); otherwise its
-    best state is kept, as the reference does.
+
+def generate_chunks(specs, config_path, allow_boundary_xpoints: bool, *, device: int | None = None,
+                    max_batch: int = MAX_BATCH):
+    """Several workers' chunks ``[(n_samples, seed), ...]`` in as few batched device solves as possible.
+
+    Returns one ``(X (n_valid, 12), Y (n_valid, nz*nr), rejected_boundary_xpoints, failed_solves)`` per spec.
+    A sample whose solve diverges counts as failed when the config sets ``solver.fail_on_diverge`` (the
+    reference's solve raises there, :103,138-140); otherwise its best state is kept, as the reference does.
     """
-    if n_samples < 0:
+    specs = [(int(n), int(seed)) for n, seed in specs]
+    if any(n < 0 for n, _ in specs):
         raise ValueError("n_samples must be >= 0")
     cfg = copy.deepcopy(_load_config(config_path))
-    if n_samples == 0:
-        return np.asarray([], dtype=np.float64), np.asarray([], dtype=np.float64), 0, 0
+    empty = (np.asarray([], dtype=np.float64), np.asarray([], dtype=np.float64), 0, 0)
+    total = sum(n for n, _ in specs)
+    if total == 0:
+        return [empty for _ in specs]
     bk = BatchedFusionKernel(cfg, device=device)
-    cc, ip = draw_perturbations(bk.cfg, n_samples, seed)
-    res = bk.solve(cc, ip, to_host=False)
-    topo = bk.topology(res["psi"])  # of the FINAL flux maps, like fk._find_magnetic_axis()/find_x_point(fk.Psi)
-    psi = res["psi"].cpu().numpy()
+    draws = [draw_perturbations(bk.cfg, n, seed) for n, seed in specs]
+    cc = np.concatenate([d[0] for d in draws])
+    ip = np.concatenate([d[1] for d in draws])
     fail_on_diverge = bool(bk.cfg["solver"].get("fail_on_diverge", False))
     r_min, r_max = float(np.min(bk.R)), float(np.max(bk.R))
     z_min, z_max = float(np.min(bk.Z)), float(np.max(bk.Z))
-    X, Y, rejected, failed = [], [], 0, 0
-    for s in range(n_samples):
-        if fail_on_diverge and int(res["status"][s]) == 3:
-            failed += 1
-            continue
-        t = topo[s]
-        if t[6] == 0.0:  # no row below 0.5*Z_min: the reference's ((0, 0), min psi) fallback
-            rx, zx, psi_x = 0.0, 0.0, float(t[7])
-        else:
-            rx, zx, psi_x = float(bk.R[int(t[4])]), float(bk.Z[int(t[3])]), float(t[5])
-        if not allow_boundary_xpoints and is_boundary_xpoint(rx, zx, r_min, r_max, z_min, z_max):
-            rejected += 1
-            continue
-        X.append([float(ip[s] / 1e6), 5.3, float(bk.R[int(t[1])]), float(bk.Z[int(t[0])]), 1.0, 1.0, float(t[2]), psi_x,
-                  1.7, 0.33, 0.33, 3.0])
-        Y.append(psi[s].ravel())
-    return np.asarray(X, dtype=np.float64), np.asarray(Y, dtype=np.float64), rejected, failed
+    rows: list = []  # per sample: None (failed), False (rejected) or (features, psi)
+    for lo in range(0, total, max_batch):
+        hi = min(total, lo + max_batch)
+        res = bk.solve(cc[lo:hi], ip[lo:hi], to_host=False)
+        topo = bk.topology(res["psi"])  # of the FINAL flux maps, like fk._find_magnetic_axis()/find_x_point(fk.Psi)
+        psi = res["psi"].cpu().numpy()
+        for s in range(hi - lo):
+            if fail_on_diverge and int(res["status"][s]) == 3:
+                rows.append(None)
+                continue
+            t = topo[s]
+            if t[6] == 0.0:  # no row below 0.5*Z_min: the reference's ((0, 0), min psi) fallback
+                rx, zx, psi_x = 0.0, 0.0, float(t[7])
+            else:
+                rx, zx, psi_x = float(bk.R[int(t[4])]), float(bk.Z[int(t[3])]), float(t[5])
+            if not allow_boundary_xpoints and is_boundary_xpoint(rx, zx, r_min, r_max, z_min, z_max):
+                rows.append(False)
+                continue
+            rows.append(([float(ip[lo + s] / 1e6), 5.3, float(bk.R[int(t[1])]), float(bk.Z[int(t[0])]), 1.0, 1.0, float(t[2]),
+                          psi_x, 1.7, 0.33, 0.33, 3.0], psi[s].ravel()))
+    out, at = [], 0
+    for n, _ in specs:
+        part = rows[at:at + n]
+        at += n
+        good = [r for r in part if r]
+        out.append((np.asarray([g[0] for g in good], dtype=np.float64), np.asarray([g[1] for g in good], dtype=np.float64),
+                    sum(1 for r in part if r is False), sum(1 for r in part if r is None)))
+    return out
+
+
+def generate_chunk(n_samples: int, config_path, seed: int, allow_boundary_xpoints: bool, *, device: int | None = None):
+    """One worker's chunk (the reference's ``generate_chunk`` signature; ``config_path``: path or dict)."""
+    return generate_chunks([(n_samples, seed)], config_path, allow_boundary_xpoints, device=device)[0]
 
 
 def chunk_plan(samples: int, workers: int) -> list[tuple[int, int]]:
@@ -112,8 +135,8 @@ def generate_dataset(config_path, samples: int, workers: int, allow_boundary_xpo
     (``torch.distributed.gather_object`` of the host arrays; the solves themselves need no collective).
     Returns ``(X, Y, rejected, failed)`` on rank 0 and ``None`` elsewhere."""
     plan = chunk_plan(samples, workers)
-    mine = {i: generate_chunk(n, config_path, seed, allow_boundary_xpoints, device=device)
-            for i, (n, seed) in enumerate(plan) if i % world == rank}
+    idx = [i for i in range(len(plan)) if i % world == rank]
+    mine = dict(zip(idx, generate_chunks([plan[i] for i in idx], config_path, allow_boundary_xpoints, device=device)))
     if world > 1:
         import torch.distributed as dist
         gathered = [None] * world if rank == 0 else None

@@ -59,6 +59,10 @@ def _fake_chunk(n, config, seed, allow, *, device=None):
     return X, Y, n - keep, 0
 
 
+def _fake_chunks(specs, config, allow, *, device=None):
+    return [_fake_chunk(n, config, seed, allow) for n, seed in specs]
+
+
 def _expected(samples, workers):
     from scpn_fusion_core_b200 import dataset as ds
     parts = [_fake_chunk(n, None, s, False) for n, s in ds.chunk_plan(samples, workers)]
@@ -69,7 +73,7 @@ def _expected(samples, workers):
 
 def test_generate_dataset_merges_chunks_in_worker_order(monkeypatch):
     from scpn_fusion_core_b200 import dataset as ds
-    monkeypatch.setattr(ds, "generate_chunk", _fake_chunk)
+    monkeypatch.setattr(ds, "generate_chunks", _fake_chunks)
     X, Y, rej, failed = ds.generate_dataset("unused", 11, 4)
     eX, eY, erej = _expected(11, 4)
     np.testing.assert_array_equal(X, eX)
@@ -84,7 +88,7 @@ def _worker(rank, world, port, out_dir):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from scpn_fusion_core_b200 import dataset as ds
     import test_dataset_cpu as me
-    ds.generate_chunk = me._fake_chunk
+    ds.generate_chunks = me._fake_chunks
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     try:
         out = ds.generate_dataset("unused", 13, 5, rank=rank, world=world)
