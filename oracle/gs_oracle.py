@@ -562,9 +562,37 @@ class PicardProblem:
         return [(c["r"], c["z"], c["current"]) for c in self.cfg["coils"]]
 
 
+def anderson_mix(psi_hist, res_hist, m=5):
+    """fusion_kernel_iterative_solver.py:248-314 - type-II Anderson mixing over the last min(m, k) iterates:
+    gamma = argmin |F_last - dF gamma| via the 1e-10-regularised normal equations, alpha from gamma
+    (alpha_last = 1 - sum gamma, alpha_j = -gamma_j, renormalised to sum 1), mixed = sum alpha_j psi_j."""
+    mk = min(m, len(res_hist))
+    if mk < 2:
+        return psi_hist[-1].copy()
+    F = np.column_stack([r.ravel() for r in res_hist[-mk:]])
+    dF = np.diff(F, axis=1)
+    gram = dF.T @ dF
+    gram += 1e-10 * np.eye(gram.shape[0])
+    try:
+        gamma = np.linalg.solve(gram, dF.T @ F[:, -1])
+    except np.linalg.LinAlgError:
+        return psi_hist[-1].copy()
+    a = np.zeros(mk)
+    a[-1] = 1.0 - np.sum(gamma)
+    a[:-1] -= gamma
+    tot = np.sum(a)
+    if abs(tot) < 1e-12:
+        return psi_hist[-1].copy()
+    a /= tot
+    mixed = np.zeros_like(psi_hist[-1])
+    for j, p in enumerate(psi_hist[-mk:]):
+        mixed += a[j] * p
+    return mixed
+
+
 def picard_solve(prob: PicardProblem, *, preserve_initial_state=False, boundary_flux=None,
                  trace=None) -> dict[str, Any]:
-    """fusion_kernel_newton_solver.py:390-615 (methods multigrid/sor/jacobi; no anderson/newton).
+    """fusion_kernel_newton_solver.py:390-615 (methods multigrid/sor/jacobi/anderson; no newton).
 
     ``trace`` (a list) receives per-iteration dicts of intermediates for tests.
     """
@@ -572,8 +600,8 @@ def picard_solve(prob: PicardProblem, *, preserve_initial_state=False, boundary_
     cfg = prob.cfg
     sol = cfg["solver"]
     method = sol.get("solver_method", "multigrid")
-    if method not in ("multigrid", "sor", "jacobi"):
-        raise ValueError(f"oracle covers multigrid/sor/jacobi, not {method!r}")
+    if method not in ("multigrid", "sor", "jacobi", "anderson"):
+        raise ValueError(f"oracle covers multigrid/sor/jacobi/anderson, not {method!r}")
     ip = cfg["physics"]["plasma_current_target"]
     mu0 = cfg["physics"]["vacuum_permeability"]
     if abs(ip) < 1e-12 and not preserve_initial_state:
@@ -609,6 +637,8 @@ def picard_solve(prob: PicardProblem, *, preserve_initial_state=False, boundary_
         raise ValueError("solver.gs_residual_threshold must be > 0")
     saddle = bool(sol.get("xpoint_use_saddle_detection", False))
 
+    depth = sol.get("anderson_depth", 5)
+    psi_hist, res_hist = [], []
     best = prob.Psi.copy()
     diff_best = 1e9
     hist, gs_hist = [], []
@@ -657,6 +687,16 @@ def picard_solve(prob: PicardProblem, *, preserve_initial_state=False, boundary_
         diff = float(np.mean(np.abs(new - prob.Psi)))
         hist.append(diff)
         prob.Psi = (1.0 - alpha) * prob.Psi + alpha * new
+        if method == "anderson":  # fusion_kernel_newton_solver.py:539-550
+            psi_hist.append(prob.Psi.copy())
+            res_hist.append(new - prob.Psi)
+            if len(psi_hist) >= 3 and k % 3 == 0:
+                mixed = anderson_mix(psi_hist, res_hist, depth)
+                copy_wall(mixed, bc)
+                prob.Psi = mixed
+            if len(psi_hist) > depth + 2:
+                psi_hist.pop(0)
+                res_hist.pop(0)
         gsr = gs_residual_rms(prob.Psi, src, prob.RR, prob.dR, prob.dZ)
         gs_hist.append(gsr)
         gs_best = min(gs_best, gsr)

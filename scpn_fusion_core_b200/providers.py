@@ -10,6 +10,9 @@ cross-tier agreement is no longer f32-bounded.
 ``PyGpuSolver`` / ``py_gpu_available`` / ``py_gpu_info`` reproduce the surface of the
 reference's PyO3 module ``scpn_fusion_rs`` (``fusion-python/src/bindings/gpu.rs:19-90``) so an
 UNMODIFIED ``bench_gpu_gs_solver.py`` can be pointed at this package.
+``PyFusionKernel`` / ``PyEquilibriumResult`` / ``multigrid_vcycle`` are the equilibrium names of the same
+module (``fusion-python/src/bindings/equilibrium.rs:14-116,368-401``), i.e. what the reference's Rust tier
+(``_rust_compat.RustAcceleratedKernel``, ``_multi_compat_providers._rust_multigrid_solve``) binds.
 """
 from __future__ import annotations
 
@@ -87,6 +90,90 @@ class PyGpuSolver:
         s = np.asarray(source, dtype=np.float64).reshape(self.nz, self.nr)
         out = _gpu_gs_rb_sor_smooth(p, s, *self.box, omega=omega, n_sweeps=int(iterations))
         return out.astype(np.float32).ravel()
+
+
+class PyEquilibriumResult:
+    """Read-only result record of ``PyFusionKernel.solve_equilibrium`` (``bindings/equilibrium.rs:119-152``)."""
+
+    __slots__ = ("converged", "iterations", "residual", "axis_r", "axis_z", "x_point_r", "x_point_z", "psi_axis",
+                 "psi_boundary", "solve_time_ms")
+
+    def __init__(self, **kw: Any) -> None:
+        for k in self.__slots__:
+            object.__setattr__(self, k, kw[k])
+
+    def __setattr__(self, name: str, value: Any) -> None:
+        raise AttributeError("PyEquilibriumResult is read-only")
+
+    def __repr__(self) -> str:
+        return f"EquilibriumResult(converged={self.converged}, iters={self.iterations}, residual={self.residual:.2e})"
+
+
+class PyFusionKernel:
+    """Surface of the reference's PyO3 ``PyFusionKernel`` (``bindings/equilibrium.rs:14-116``) on the B200.
+
+    The arithmetic is this package's ``FusionKernel`` (parity with the reference's NumPy lane; the Rust lane
+    itself differs from NumPy in documented details).  ``calculate_thermodynamics`` is not part
+    of the equilibrium path and raises ``NotImplementedError``.
+    """
+
+    _METHODS = {"sor": "sor", "picard_sor": "sor", "multigrid": "multigrid", "picard_multigrid": "multigrid", "mg": "multigrid"}
+
+    def __init__(self, config_path: str) -> None:
+        from .fusion_kernel import FusionKernel
+        try:
+            self._k = FusionKernel(str(config_path))
+        except (FileNotFoundError, ValueError, KeyError) as exc:  # PyO3 maps every load failure to PyIOError
+            raise OSError(str(exc)) from exc
+
+    def solve_equilibrium(self) -> PyEquilibriumResult:
+        import time
+        t0 = time.perf_counter()
+        try:
+            r = self._k.solve_equilibrium()
+        except Exception as exc:  # PyO3: PyRuntimeError(e.to_string())
+            raise RuntimeError(str(exc)) from exc
+        iz, ir, psi_ax = self._k._find_magnetic_axis()
+        (rx, zx), psi_b = self._k.find_x_point(self._k.Psi)
+        return PyEquilibriumResult(converged=bool(r["converged"]), iterations=int(r["iterations"]), residual=float(r["residual"]),
+                                   axis_r=float(self._k.R[ir]), axis_z=float(self._k.Z[iz]), x_point_r=float(rx),
+                                   x_point_z=float(zx), psi_axis=float(psi_ax), psi_boundary=float(psi_b),
+                                   solve_time_ms=(time.perf_counter() - t0) * 1e3)
+
+    def calculate_thermodynamics(self, p_aux_mw: float):
+        raise NotImplementedError("calculate_thermodynamics is outside the B200 equilibrium path (SURVEY.md 8)")
+
+    def get_psi(self) -> np.ndarray:
+        return np.array(self._k.Psi, dtype=np.float64, copy=True)
+
+    def get_j_phi(self) -> np.ndarray:
+        return np.array(self._k.J_phi, dtype=np.float64, copy=True)
+
+    def get_r(self) -> np.ndarray:
+        return np.array(self._k.R, dtype=np.float64, copy=True)
+
+    def get_z(self) -> np.ndarray:
+        return np.array(self._k.Z, dtype=np.float64, copy=True)
+
+    def grid_shape(self) -> tuple[int, int]:
+        return int(self._k.NR), int(self._k.NZ)
+
+    def set_solver_method(self, method: str) -> None:
+        m = self._METHODS.get(str(method).lower())
+        if m is None:
+            raise ValueError(f"Unknown solver method '{method}'. Use 'sor' or 'multigrid'.")
+        self._k.cfg["solver"]["solver_method"] = m
+
+    def solver_method(self) -> str:
+        m = self._k.cfg["solver"].get("solver_method", "multigrid")
+        return "sor" if m == "sor" else "multigrid"
+
+
+def multigrid_vcycle(source: Any, psi_bc: Any, r_min: float, r_max: float, z_min: float, z_max: float, nr: int, nz: int,
+                     tol: float = 1e-6, max_cycles: int = 500):
+    """``scpn_fusion_rs.multigrid_vcycle`` (``bindings/equilibrium.rs:368-401``): despite the name a full
+    V-cycle solve, positional ``tol`` / ``max_cycles``; returns ``(psi, residual, cycles, converged)``."""
+    return _gpu_multigrid_solve(source, psi_bc, r_min, r_max, z_min, z_max, int(nr), int(nz), tol=tol, max_cycles=int(max_cycles))
 
 
 def register(multi: Any) -> None:

@@ -462,6 +462,23 @@ def gen_eqdsk():
     _save("eqdsk", **out)
 
 
+def gen_anderson():
+    """solver_method="anderson" (SOR inner sweep + Anderson mixing every third iterate)."""
+    out = {}
+    for tag, name, n, kw in (("val33", "iter_validated_config.json", 33, {}),
+                             ("iter49", "iter_config.json", 49, {"anderson_depth": 3, "max_iterations": 200})):
+        cfg = _cfg(name, n, solver_method="anderson", **kw)
+        k = _kernel(cfg)
+        r = k.solve_equilibrium()
+        out[tag + "_cfg"] = np.array(json.dumps(cfg))
+        out[tag + "_psi"] = k.Psi.copy()
+        out[tag + "_meta"] = np.array([r["iterations"], float(r["converged"]), r["residual"], r["gs_residual"]])
+        out[tag + "_hist"] = np.array(r["residual_history"])
+        out[tag + "_gshist"] = np.array(r["gs_residual_history"])
+        print(f"  {tag}: its={r['iterations']} conv={r['converged']} res={r['residual']:.3e}")
+    _save("anderson", **out)
+
+
 # -- 7. the reference's compiled C++ solver (hpc/solver.cpp) ----------------------
 
 def gen_hpc():
@@ -505,7 +522,7 @@ def gen_elliptic():
 
 if __name__ == "__main__":
     which = sys.argv[1:] or ["ops", "mg_solve", "bench_smooth", "picard_pieces", "solves",
-                             "solve_129_validated", "free_boundary", "free_boundary_shape", "dataset", "eqdsk", "hpc", "elliptic"]
+                             "solve_129_validated", "free_boundary", "free_boundary_shape", "dataset", "eqdsk", "anderson", "hpc", "elliptic"]
     for w in which:
         print("==", w)
         globals()["gen_" + w]()

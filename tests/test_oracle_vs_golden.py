@@ -282,6 +282,29 @@ def test_magnetic_probe_response_and_reconstruction():
         G.probe_response_matrix(pos, [1] * len(pos), b_probe_points=z["probe_b_pts"], b_probe_directions=["R", "Q", "R", "R", "R", "R"])
 
 
+@pytest.mark.parametrize("tag", ["val33", "iter49"])
+def test_anderson_method(tag):
+    """SURVEY.md 8f row 4 (oracle only so far): SOR sweep + Anderson mixing every third iterate.  The Gram
+    matrix goes through BLAS, so a different BLAS build may round it differently: the early history is held
+    tightly, the end state (200-1000 non-contractive iterations later) loosely."""
+    import json
+    z = golden("anderson")
+    prob = G.PicardProblem(json.loads(str(z[tag + "_cfg"])))
+    r = G.picard_solve(prob)
+    assert r["iterations"] == int(z[tag + "_meta"][0]) and r["converged"] == bool(z[tag + "_meta"][1])
+    np.testing.assert_allclose(r["residual_history"][:12], z[tag + "_hist"][:12], rtol=1e-10)
+    np.testing.assert_allclose(r["gs_residual_history"][:12], z[tag + "_gshist"][:12], rtol=1e-10)
+    assert rel_l2(r["psi"], z[tag + "_psi"]) <= 1e-6
+    # the mixing step alone: two-iterate history returns the affine combination, one iterate returns a copy
+    a, b = np.ones((4, 5)), np.full((4, 5), 3.0)
+    np.testing.assert_array_equal(G.anderson_mix([a], [b], 5), a)
+    ra, rb = np.full((4, 5), 2.0), np.full((4, 5), 1.0)
+    # gamma = dF.F_last/(dF.dF) = -1 -> alpha = [-gamma, 1 - gamma]/sum = [1/3, 2/3] (the reference's own
+    # coefficient convention, fusion_kernel_iterative_solver.py:296-303, not the textbook extrapolation)
+    mixed = G.anderson_mix([a, b], [ra, rb], 5)
+    np.testing.assert_allclose(mixed, np.full((4, 5), 7.0 / 3.0), rtol=1e-8)
+
+
 def test_hpc_cpp_arithmetic():
     """oracle.hpc_run_step vs the compiled reference solver.cpp (FMA contraction allowed there)."""
     z = golden("hpc_solver")
