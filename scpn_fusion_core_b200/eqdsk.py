@@ -7,6 +7,9 @@ fixed-width ``5e16.9`` numbers, including run-together values such as ``2.385E+0
 same ``to_config()`` dictionary (``eqdsk.py:128-186``) that seeds a ``FusionKernel`` with the EFIT
 boundary as an isoflux shape target.  ``from_kernel`` goes the other way: a solved ``FusionKernel`` ->
 ``GEqdsk`` ready to write.  Pure host-side IO; nothing here touches the GPU.
+
+Format limit shared with the reference: a value with a three-digit decimal exponent fills all 24 columns of its
+cell, so neighbouring cells run together and cannot be split again; keep |x| within [1e-99, 1e99] (or 0).
 """
 from __future__ import annotations
 
