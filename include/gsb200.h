@@ -269,7 +269,9 @@ int gsb_halo_recv(double *halo_up, double *halo_dn, long long n, const double *i
 
 /* Native driver of the distributed levels of one slab V-cycle: every launch of the descent
  * (gsb_slab_down) and of the ascent (gsb_slab_up) is issued from one call; the host gathers the
- * coarsest distributed right-hand side and runs the replicated coarse V-cycle in between. */
+ * coarsest distributed right-hand side and runs the replicated coarse V-cycle in between.  Together they
+ * are the recursion of multigrid_vcycle (multigrid_solve.py:252-335) on one rank's Z-row slab (the
+ * reference's decompose_z partition, mpi_domain.rs:48); halo = NULL on a single rank. */
 typedef struct gsb_slab_level_desc {
   gsb_ctx *ctx;              /* slab context of the level (rows_loc x nr) */
   double *x, *f, *alt, *cur; /* solution, right-hand side, ping-pong partner (NULL if single tile), live buffer */
