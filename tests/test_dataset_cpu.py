@@ -111,3 +111,75 @@ def test_generate_dataset_two_ranks(tmp_path):
     s.close()
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert os.path.exists(tmp_path / "ok0") and os.path.exists(tmp_path / "ok1")
+
+
+class _OracleBatchedKernel:
+    """CPU stand-in for BatchedFusionKernel (the device solve and topology launch replaced by the oracle): lets the
+    product's chunk assembly - draw order, boundary rejection, feature rows, chunk splitting - run on CPU."""
+
+    def __init__(self, cfg, device=None):
+        from scpn_fusion_core_b200.fusion_kernel import validate_config
+        self.cfg = validate_config(cfg)
+        p = G.PicardProblem(self.cfg)
+        self.R, self.Z = p.R, p.Z
+
+    def solve(self, cc, ip, to_host=False):
+        import copy
+        psi, status = [], []
+        for s in range(cc.shape[0]):
+            cfg = copy.deepcopy(self.cfg)
+            for c, cur in zip(cfg["coils"], cc[s]):
+                c["current"] = float(cur)
+            cfg["physics"]["plasma_current_target"] = float(ip[s])
+            prob = G.PicardProblem(cfg)
+            r = G.picard_solve(prob)
+            psi.append(prob.Psi.copy())
+            status.append(1 if r["converged"] else 2)
+        return {"psi": _FakeDeviceArray(np.stack(psi)), "status": np.array(status)}
+
+    def topology(self, psi_dev):
+        out = np.zeros((psi_dev.a.shape[0], 8))
+        p = G.PicardProblem(self.cfg)
+        for s, psi in enumerate(psi_dev.a):
+            iz, ir, pax = G.find_axis(psi)
+            (rx, zx), px = G.find_x_point(psi, p.R, p.Z, p.dR, p.dZ, self.cfg["dimensions"]["Z_min"])
+            found = not (rx == 0.0 and zx == 0.0)
+            izx = int(np.argmin(np.abs(p.Z - zx))) if found else 0
+            irx = int(np.argmin(np.abs(p.R - rx))) if found else 0
+            out[s] = [iz, ir, pax, izx, irx, px, 1.0 if found else 0.0, float(np.min(psi))]
+        return out
+
+
+class _FakeDeviceArray:
+    def __init__(self, a):
+        self.a = a
+
+    def cpu(self):
+        return self
+
+    def numpy(self):
+        return self.a
+
+
+def test_chunk_assembly_matches_reference_with_oracle_backed_kernel(monkeypatch):
+    from scpn_fusion_core_b200 import dataset as ds
+    monkeypatch.setattr(ds, "BatchedFusionKernel", _OracleBatchedKernel)
+    z = golden("dataset")
+    for tag in ("iter", "iter_allow"):
+        n, seed, allow, rej, failed = (int(v) for v in z[tag + "_meta"])
+        X, Y, r, f = ds.generate_chunk(n, json.loads(str(z[tag + "_cfg"])), seed, bool(allow))
+        assert (r, f) == (rej, failed) and X.shape == z[tag + "_X"].shape
+        if X.size:
+            np.testing.assert_allclose(X, z[tag + "_X"], rtol=1e-12, atol=0)
+            assert rel_l2(Y, z[tag + "_Y"]) <= 1e-13
+    # two specs in one call = the two chunks computed separately
+    cfg = json.loads(str(z["iter_allow_cfg"]))
+    both = ds.generate_chunks([(1, 43), (1, 44)], cfg, True)
+    one = ds.generate_chunk(1, cfg, 44, True)
+    np.testing.assert_array_equal(both[1][0], one[0])
+    np.testing.assert_array_equal(both[1][1], one[1])
+    np.testing.assert_array_equal(both[0][0], z["iter_allow_X"][:1])
+    with pytest.raises(ValueError):
+        ds.generate_chunks([(-1, 42)], cfg, True)
+    empty = ds.generate_chunks([(0, 42)], cfg, True)[0]
+    assert empty[0].size == 0 and empty[2:] == (0, 0)
