@@ -479,6 +479,37 @@ def gen_anderson():
     _save("anderson", **out)
 
 
+def gen_solovev():
+    """validation/validate_grad_shafranov_solovev.py re-run here (operator truncation error, SOR reconstruction,
+    NumPy-tier multigrid reconstruction of psi = c1 R^4/8 + c2 Z^2) next to the numbers of the reference's sealed
+    report validation/reports/grad_shafranov_solovev.json."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_solovev", os.path.join(REF, "validation", "validate_grad_shafranov_solovev.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["ref_solovev"] = mod
+    spec.loader.exec_module(mod)
+    geo = mod.SolovevGeometry.from_aspect()
+    sealed = json.load(open(os.path.join(REF, "validation", "reports", "grad_shafranov_solovev.json")))
+    out = {"geometry": {k: getattr(geo, k) for k in ("r0", "a", "r_min", "r_max", "z_min", "z_max", "c1", "c2")},
+           "sealed": {k: sealed[k] for k in ("operator_records", "operator_order", "reconstruction_records",
+                                             "multigrid_numpy_record", "operator_error_gate", "reconstruction_nrmse_gate")}}
+    out["operator_errors"] = {str(n): mod.operator_truncation_error(geo, n) for n in (33, 49, 65, 97)}
+    out["sor"] = {}
+    for n in (33, 49):
+        r = mod.sor_reconstruction(geo, n)
+        out["sor"][str(n)] = {"nrmse": r.nrmse, "iterations": r.iterations, "converged": r.converged, "residual_inf": r.residual_inf}
+    m = mod.dispatched_multigrid_reconstruction(geo, 97, tier="numpy", analytic_tolerance=1e-4)
+    out["multigrid_numpy_97"] = {"nrmse": m.nrmse, "residual": m.residual, "cycles": m.cycles, "converged": m.converged}
+    for n in (33, 49, 65, 97):
+        sealed_err = [r["error"] for r in sealed["operator_records"] if r["resolution"] == n][0]
+        print(f"  operator {n}: here {out['operator_errors'][str(n)]:.16e} sealed {sealed_err:.16e}")
+    print("  sor:", out["sor"], "\n  mg:", out["multigrid_numpy_97"], "sealed", sealed["multigrid_numpy_record"])
+    path = os.path.join(HERE, "solovev.json")
+    with open(path, "w") as f:
+        json.dump(out, f, indent=1, sort_keys=True)
+    print("wrote solovev.json")
+
+
 # -- 7. the reference's compiled C++ solver (hpc/solver.cpp) ----------------------
 
 def gen_hpc():
@@ -522,7 +553,7 @@ def gen_elliptic():
 
 if __name__ == "__main__":
     which = sys.argv[1:] or ["ops", "mg_solve", "bench_smooth", "picard_pieces", "solves",
-                             "solve_129_validated", "free_boundary", "free_boundary_shape", "dataset", "eqdsk", "anderson", "hpc", "elliptic"]
+                             "solve_129_validated", "free_boundary", "free_boundary_shape", "dataset", "eqdsk", "anderson", "solovev", "hpc", "elliptic"]
     for w in which:
         print("==", w)
         globals()["gen_" + w]()
