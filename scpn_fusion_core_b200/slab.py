@@ -586,14 +586,21 @@ class SlabMultigrid:
                     torch.cuda.synchronize()
                     g = torch.cuda.CUDAGraph()
                     try:
-                        with torch.cuda.graph(g):
+                        # thread_local: the NCCL watchdog thread may query events while this thread captures
+                        with torch.cuda.graph(g, capture_error_mode="thread_local" if comm.world > 1 else "global"):
                             x2 = cycle(x)
                         if x2.data_ptr() == x.data_ptr():
-                            graph = st["graph"] = g
+                            graph = g
                     except Exception:
                         if self.strict_graph:
                             raise
                         graph = None
+                    if comm.world > 1:
+                        # all ranks replay or none does: a rank whose capture failed would otherwise issue the
+                        # cycle eagerly against peers replaying it
+                        if comm.max(0.0 if graph is not None else 1.0) > 0.0:
+                            graph = None
+                    st["graph"] = graph
                     want_graph = graph is not None
             residual = comm.max(ops.residual_linf(L, x, f, r0, r1))
             cycles += 1
