@@ -135,3 +135,51 @@ def test_config_validation_matches_reference_schema():
     ):
         with pytest.raises(ValueError):
             validate_config(bad)
+
+
+def _header_prototypes():
+    """name -> (return type, [parameter type strings]) parsed from include/gsb200.h."""
+    text = open(os.path.join(ROOT, "include", "gsb200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"typedef struct[^{;]*\{.*?\}\s*\w+\s*;", "", text, flags=re.S)
+    protos = {}
+    for ret, name, args in re.findall(r"\b((?:const\s+)?(?:unsigned\s+)?[a-z_][a-z0-9_ ]*?\s*\**)\s*\b([a-z_][a-z0-9_]*)\s*\(([^()]*)\)\s*;",
+                                      text, flags=re.S):
+        params = [a.strip() for a in args.replace("\n", " ").split(",")] if args.strip() not in ("", "void") else []
+        protos[name] = (" ".join(ret.split()), [" ".join(p.split()) for p in params])
+    return protos
+
+
+def _c_kind(decl: str) -> str:
+    """'ptr', 'double', 'int' or 'longlong' for a C parameter / return declaration."""
+    if "*" in decl:
+        return "ptr"
+    words = [w for w in re.split(r"\W+", decl) if w and w != "const"]
+    if "double" in words:
+        return "double"
+    if words[:2] == ["long", "long"]:
+        return "longlong"
+    if "void" in words:
+        return "void"
+    return "int"
+
+
+def _ctypes_kind(t) -> str:
+    if t is None:
+        return "void"
+    if t in (ctypes.c_void_p, ctypes.c_char_p) or hasattr(t, "_type_") and isinstance(getattr(t, "_type_", None), type):
+        return "ptr"
+    return {ctypes.c_double: "double", ctypes.c_int: "int", ctypes.c_longlong: "longlong"}.get(t, "ptr")
+
+
+def test_ctypes_signatures_agree_with_the_header_prototypes():
+    """A ctypes table that drifts from the header corrupts arguments silently: arity and the kind of every
+    parameter (pointer / double / int / long long) and of the return value must match include/gsb200.h."""
+    protos = _header_prototypes()
+    assert set(_lib.SIGNATURES) <= set(protos), sorted(set(_lib.SIGNATURES) - set(protos))
+    for name, (restype, argtypes) in _lib.SIGNATURES.items():
+        ret, params = protos[name]
+        assert len(argtypes) == len(params), f"{name}: {len(argtypes)} ctypes arguments vs {len(params)} in the header"
+        assert _ctypes_kind(restype) == _c_kind(ret), f"{name}: return type {restype} vs '{ret}'"
+        for i, (t, decl) in enumerate(zip(argtypes, params)):
+            assert _ctypes_kind(t) == _c_kind(decl), f"{name} argument {i}: {t} vs '{decl}'"
