@@ -183,3 +183,33 @@ def test_ctypes_signatures_agree_with_the_header_prototypes():
         assert _ctypes_kind(restype) == _c_kind(ret), f"{name}: return type {restype} vs '{ret}'"
         for i, (t, decl) in enumerate(zip(argtypes, params)):
             assert _ctypes_kind(t) == _c_kind(decl), f"{name} argument {i}: {t} vs '{decl}'"
+
+
+def test_ctypes_struct_layouts_match_the_c_header(tmp_path):
+    """sizeof / offsetof of every struct that crosses the ABI, from a C program compiled against
+    include/gsb200.h with the system gcc, against the ctypes mirrors."""
+    import shutil
+    import subprocess
+    from scpn_fusion_core_b200 import slab
+    if shutil.which("gcc") is None:
+        pytest.skip("no C compiler")
+    mirrors = {"gsb_profile": _lib.gsb_profile, "gsb_picard_params": _lib.gsb_picard_params,
+               "gsb_slab_level_desc": slab._LevelDesc, "gsb_slab_halo_desc": slab._HaloDesc}
+    lines = []
+    for cname, cls in mirrors.items():
+        lines.append(f'printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    src = tmp_path / "probe.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "gsb200.h"\nint main(void) {\n' + "\n".join(lines)
+                   + "\nreturn 0;\n}\n")
+    exe = tmp_path / "probe"
+    subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = {}
+    for ln in subprocess.check_output([str(exe)], text=True).splitlines():
+        cname, key, val = ln.split()
+        got[(cname, key)] = int(val)
+    for cname, cls in mirrors.items():
+        assert got[(cname, "size")] == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert got[(cname, fname)] == getattr(cls, fname).offset, f"{cname}.{fname}"
