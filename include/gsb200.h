@@ -189,6 +189,32 @@ int gsb_picard_solve(gsb_ctx *ctx, const gsb_picard_params *p, double *psi_dev, 
 /* Picard iterations launched by the last gsb_picard_solve on this ctx (host count). */
 int gsb_picard_last_launched_iterations(gsb_ctx *ctx);
 
+typedef struct gsb_free_boundary_params {
+  int max_outer_iter;  /* solve_free_boundary(max_outer_iter=20) */
+  double tol;          /* solve_free_boundary(tol=1e-4): stop an equilibrium when max|Psi - Psi_old| < tol */
+  int warm_j;          /* 1: jphi_dev holds a current density on entry and the plasma wall flux of outer iteration 0
+                          is formed from it; 0: outer iteration 0 sees the coil flux alone */
+} gsb_free_boundary_params;
+
+/* a17 batched: the free-boundary outer loop of solve_free_boundary (fusion_kernel_free_boundary.py:623-739,
+ * optimize_shape=False) for `batch` independent equilibria, entirely on the device.  Per outer iteration and
+ * per not-yet-converged equilibrium: wall ring of Psi <- psi_ext ring (:652-655), Psi_old <- Psi (:658), warm-started
+ * re-seeded Picard solve with that boundary map (:659-662, gsb_picard_solve semantics), diff = max|Psi - Psi_old|,
+ * stop when diff < tol (:708-711).  The host reads one counter per OUTER iteration.
+ * psi_dev      [batch][nz][nr] in: starting flux (zeros for a fresh kernel), out: solution
+ * psi_ext_dev  [batch][nz][nr] coil flux (compute_external_flux, :83-93; only its wall ring is read)
+ * wall_m_dev   NULL (lane A: the wall carries coil flux only, as in the reference's NumPy lane) or the lane-C
+ *              response matrix of gsb_wall_matrix: from outer iteration 1 on the wall gets
+ *              psi_ext + M @ (J_phi[interior]*dR*dZ) (jax_free_boundary_predictive.py:443-498) with the J_phi of the
+ *              previous inner solve, as ONE FP64 tensor-core GEMM over the batch (gsb_wall_flux)
+ * summary_dev  [batch][16] gsb_picard_solve summary of the LAST inner solve of each equilibrium
+ * fb_summary_dev [batch][4] out: outer_iterations, final_diff, Picard iterations summed over the outer
+ *              iterations, converged (final_diff < tol) */
+int gsb_free_boundary_solve(gsb_ctx *ctx, const gsb_picard_params *p, const gsb_free_boundary_params *fb,
+                            double *psi_dev, const double *psi_ext_dev, const double *wall_m_dev,
+                            const double *ip_dev, const double *prof_dev, double *jphi_dev, double *summary_dev,
+                            double *fb_summary_dev, int batch, void *stream);
+
 /* compute_b_field (fusion_kernel.py:450-456): np.gradient + 1/max(R,1e-6). */
 int gsb_b_field(gsb_ctx *ctx, const double *psi_dev, double *br_dev, double *bz_dev, int batch,
                 void *stream);

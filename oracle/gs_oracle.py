@@ -931,23 +931,37 @@ def reconstruct_currents_from_probes(response, target, prior, *, sigma=None, lim
 def free_boundary_solve(prob: PicardProblem, positions, currents, turns, *, max_outer_iter=20,
                         tol=1e-4, optimize_shape=False, tikhonov_alpha=1e-4, target_points=None,
                         target_values=None, current_limits=None, limiter_points=None, axis_point=None,
-                        x_points=None) -> dict[str, Any]:
+                        x_points=None, plasma_wall=None, wall_history=None) -> dict[str, Any]:
     """fusion_kernel_free_boundary.py:623-739.
 
     Outer loop: coil flux on the wall -> warm-started Picard -> (optional) bounded re-fit of the coil
     currents to the shape-control points -> max|dPsi| < tol; then the wall-contour reconstruction.
+
+    ``plasma_wall`` = (M, b_idx, s_idx) from ``wall_response_matrix`` adds the plasma's own flux to the wall
+    of every outer iteration after the first: wall = coil flux + M @ (J_phi[interior]*dA) with the J_phi of
+    the previous inner solve (the lane-C boundary term, jax_free_boundary_predictive.py:443-498, inside the
+    lane-A outer loop).  The reference has no such combination on its NumPy lane: PARITY UNPINNED, this
+    restatement is the only checker of the device path for that option.
     """
     if max_outer_iter < 1:
         raise ValueError("max_outer_iter must be >= 1.")
     if not np.isfinite(tol) or tol < 0.0:
         raise ValueError("tol must be finite and >= 0.")
     currents = np.asarray(currents, dtype=np.float64).copy()
-    psi_ext = external_flux(prob.R, prob.Z, positions, currents, turns)
+    psi_coil = external_flux(prob.R, prob.Z, positions, currents, turns)
+    psi_ext = psi_coil
     diff = float("inf")
     outer = 0
     inner = []
     shape = None
     for outer in range(max_outer_iter):
+        if plasma_wall is not None and outer > 0:
+            M, b_idx, s_idx = plasma_wall
+            wall = plasma_wall_flux(M, s_idx, prob.J_phi, prob.dR * prob.dZ)
+            psi_ext = psi_coil.copy()
+            psi_ext.reshape(-1)[b_idx] = psi_coil.reshape(-1)[b_idx] + wall
+            if wall_history is not None:
+                wall_history.append(wall.copy())
         copy_wall(prob.Psi, psi_ext)
         old = prob.Psi.copy()
         res = picard_solve(prob, preserve_initial_state=True, boundary_flux=psi_ext)
@@ -970,7 +984,7 @@ def free_boundary_solve(prob: PicardProblem, positions, currents, turns, *, max_
                      "max_abs_flux_residual": float(np.max(np.abs(r))), "active_current_bounds": active,
                      "target_flux": tgt.copy(), "achieved_flux": ach}
             currents = new
-            psi_ext = external_flux(prob.R, prob.Z, positions, currents, turns)
+            psi_coil = psi_ext = external_flux(prob.R, prob.Z, positions, currents, turns)
         diff = float(np.max(np.abs(prob.Psi - old)))
         if diff < tol:
             break

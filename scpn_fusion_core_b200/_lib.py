@@ -32,6 +32,10 @@ class gsb_picard_params(ctypes.Structure):
     ]
 
 
+class gsb_free_boundary_params(ctypes.Structure):
+    _fields_ = [("max_outer_iter", c_int), ("tol", c_double), ("warm_j", c_int)]
+
+
 _dp = POINTER(c_double)
 _ip = POINTER(c_int)
 
@@ -71,6 +75,9 @@ SIGNATURES = {
     "gsb_picard_solve": (c_int, [c_void_p, POINTER(gsb_picard_params), c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "gsb_picard_last_launched_iterations": (c_int, [c_void_p]),
+    "gsb_free_boundary_solve": (c_int, [c_void_p, POINTER(gsb_picard_params), POINTER(gsb_free_boundary_params), c_void_p,
+                                        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                        c_void_p]),
     "gsb_enable_peer_access": (c_int, [c_int, c_int]),
     "gsb_ipc_alloc": (c_int, [c_int, c_longlong, POINTER(c_void_p), c_char_p]),
     "gsb_ipc_open": (c_int, [c_int, c_char_p, POINTER(c_void_p)]),

@@ -472,11 +472,7 @@ int gsb_wall_flux(gsb_ctx *ctx, const double *m_dev, const double *jphi_dev, dou
     double *part = wall_dev;
     if (splits > 1) GSB_CUDA(cudaMallocAsync(&part, (size_t)splits * batch * nw * sizeof(double), st));
     constexpr int kBigSmem = 2 * HK * (HB + 4 + HW + 4) * (int)sizeof(double);
-    static bool attr_set = false;
-    if (!attr_set) {
-      GSB_CUDA(cudaFuncSetAttribute(k_wall_gemm_big, cudaFuncAttributeMaxDynamicSharedMemorySize, kBigSmem));
-      attr_set = true;
-    }
+    GSB_SMEM_OPT_IN(k_wall_gemm_big, kBigSmem);
     k_wall_gemm_big<<<dim3((batch + HB - 1) / HB, (nw + HW - 1) / HW, splits), 256, kBigSmem, st>>>(
         m_dev, jphi_dev, ctx->nz, ctx->nr, batch, nw, ni, dA, tps, part);
     GSB_LAUNCH_CHECK();

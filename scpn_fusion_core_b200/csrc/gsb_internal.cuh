@@ -6,8 +6,14 @@
 //     free of FMA contraction (dmul/dadd/dsub wrappers) so that results are bit-identical
 //     to NumPy wherever NumPy's own result is defined by IEEE +,-,*,/ alone
 //   * divisions by per-level / per-column constants use the Markstein sequence
-//     q = a*y; r = fma(-b,q,a); q' = fma(r,y,q) with y = RN(1/b): correctly rounded (equals
-//     IEEE a/b; validated on 2e8 random operands) at 3 FP64 issue slots instead of ~25
+//     q = a*y; r = fma(-b,q,a); q' = fma(r,y,q) with y = RN(1/b) at 3 FP64 issue slots instead of ~25.
+//     What is proven: r is exact, and before its final rounding q' equals a/b + (a/b - q)*d with
+//     d = b*y - 1, |d| <= 2^-53 and |a/b - q| < 1.5 ulp, i.e. the exact quotient perturbed by less than
+//     1.7e-16 ulp; so q' == RN(a/b) unless a/b lies that close to a rounding boundary.  A quotient of two
+//     binary64 numbers can come as close as 2^-54 ulp to a midpoint, so for a given divisor a handful of
+//     the 2^52 possible significands of `a` may round the other way (1 ulp): about 2^-51 per division,
+//     never seen in 2e8 random operand pairs nor in any parity test, and 7 orders of magnitude inside the
+//     1e-9 tolerance.  Exact for power-of-two divisors (d = 0).
 #pragma once
 
 #include <cuda_runtime.h>
@@ -26,6 +32,7 @@ namespace gsb {
 // ---------------------------------------------------------------- errors / launch count
 void set_error(const std::string &msg);
 extern std::atomic<long long> g_launches;
+constexpr int kMaxDevices = 64;
 
 #define GSB_CUDA(call)                                                                      \
   do {                                                                                      \
@@ -54,14 +61,28 @@ extern std::atomic<long long> g_launches;
     }                                                                                       \
   } while (0)
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device (per-context) attribute: opt a kernel in
+// once per device, not once per process (one process may drive several GPUs, and from several threads).
+#define GSB_SMEM_OPT_IN(kernel, bytes)                                                      \
+  do {                                                                                      \
+    static std::atomic<bool> _done[gsb::kMaxDevices];                                       \
+    int _dev = 0;                                                                           \
+    GSB_CUDA(cudaGetDevice(&_dev));                                                         \
+    if (_dev < 0 || _dev >= gsb::kMaxDevices || !_done[_dev].load(std::memory_order_acquire)) { \
+      GSB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+      if (_dev >= 0 && _dev < gsb::kMaxDevices) _done[_dev].store(true, std::memory_order_release); \
+    }                                                                                       \
+  } while (0)
+
 // ---------------------------------------------------------------- exact FP64 helpers
 __device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
 __device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
-// a / b with y = RN(1/b) precomputed: q = a*y; r = fma(-b,q,a); q' = fma(r,y,q) equals the IEEE
-// quotient for finite operands whose quotient neither overflows nor is subnormal (validated on
-// 2e8 random pairs).  A non-finite q (inf/NaN input or overflow) is returned as is, which is the
-// IEEE result as well (+-inf keeps its sign, NaN stays NaN) - branch free.
+// a / b with y = RN(1/b) precomputed: q = a*y; r = fma(-b,q,a); q' = fma(r,y,q).  Equals the IEEE
+// quotient except for the ~2^-51 fraction of dividends whose exact quotient sits within 1.7e-16 ulp of
+// a rounding boundary (see the header of this file); finite operands, no overflow / subnormal quotient.
+// A non-finite q (inf/NaN input or overflow) is returned as is, which is the IEEE result as well
+// (+-inf keeps its sign, NaN stays NaN) - branch free.
 __device__ __forceinline__ double ddiv_y(double a, double b, double y) {
   const double q = __dmul_rn(a, y);
   const double r = __fma_rn(-b, q, a);

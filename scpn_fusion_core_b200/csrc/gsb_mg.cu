@@ -399,11 +399,7 @@ static int base_solve_launch(const LevelGeom &g, double *x, size_t xstride, cons
     if (zero_init) GSB_CUDA(cudaMemsetAsync(x, 0, (size_t)batch * xstride * sizeof(double), st));
     return smooth_launch(g, x, xstride, rhs, rstride, batch, omega, sweeps, 0, active, st);
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    GSB_CUDA(cudaFuncSetAttribute(k_base_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, kBaseSmemMax));
-    attr_set = true;
-  }
+  GSB_SMEM_OPT_IN(k_base_solve, kBaseSmemMax);
   k_base_solve<<<batch, 128, smem, st>>>(g, x, xstride, rhs, rstride, zero_init, omega, 1.0 - omega, sweeps, active);
   GSB_LAUNCH_CHECK();
   return GSB_OK;
@@ -509,11 +505,7 @@ static int resident_launch(gsb_ctx *ctx, int l0, double *x, size_t xstride, cons
     set_error("resident_launch: plan does not fit shared memory");
     return GSB_EINVAL;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    GSB_CUDA(cudaFuncSetAttribute(k_vcycle_resident, cudaFuncAttributeMaxDynamicSharedMemorySize, kResSmemMax));
-    attr_set = true;
-  }
+  GSB_SMEM_OPT_IN(k_vcycle_resident, kResSmemMax);
   const size_t smem = (size_t)(plan.pool_doubles + res_stage_doubles(plan.nlev)) * sizeof(double);
   const int grid = std::min(batch, ctx->num_sms);
   k_vcycle_resident<<<grid, kResThreads, smem, st>>>(plan, x, xstride, rhs_split, zero_init, batch, omega, pre, post, active);

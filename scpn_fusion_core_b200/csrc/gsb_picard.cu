@@ -603,17 +603,18 @@ __global__ void k_decide(PicardState s, const double *__restrict__ rpart, int P,
 }
 
 __global__ void k_picard_init(PicardState s, int batch, int best0, const double *__restrict__ ip,
-                              int seed) {
+                              int seed, const int *__restrict__ mask) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= batch) return;
-  s.active[b] = 1;
+  const int on = mask ? (mask[b] != 0) : 1;  // masked-out equilibria are left untouched by the whole solve
+  s.active[b] = on;
   s.status[b] = 0;
   s.iter[b] = 0;
   s.cur[b] = 0;
   s.best[b] = best0;
   s.nxt[b] = 1;
   s.xsel[b] = -1;
-  s.seed_active[b] = (seed && fabs(ip[b]) >= 1e-12) ? 1 : 0;
+  s.seed_active[b] = (on && seed && fabs(ip[b]) >= 1e-12) ? 1 : 0;
   s.diff_best[b] = 1e9;
   s.gs_best[b] = INFINITY;
   s.gs_last[b] = INFINITY;
@@ -638,8 +639,10 @@ k_seed_source(size_t n, int nr, const double *__restrict__ seedJ, double seed_su
 }
 
 __global__ void __launch_bounds__(256)
-k_finalize(Bufs bufs, PicardState s, size_t n, double *__restrict__ summary, int batch) {
+k_finalize(Bufs bufs, PicardState s, size_t n, double *__restrict__ summary, int batch,
+           const int *__restrict__ mask) {
   const int b = blockIdx.y;
+  if (mask && !mask[b]) return;
   const int c = s.cur[b];
   if (c != 0) {
     const double *f = bufs.p[c] + (size_t)b * n;
@@ -721,6 +724,8 @@ struct PicardResArgs {
   ProfileDev prof;
   int scratch_off;          // pool offset (doubles) of 96 doubles of reduction / broadcast scratch
   int tplane_off;           // pool offset of a spare half plane (Jacobi seed)
+  const int *order;         // NULL, or the compacted list of equilibria to solve (free-boundary outer loop)
+  const int *n_order;       // device count of entries in `order`
 };
 
 __device__ __forceinline__ double pl(int xo, int nz, int hw, int iz, int ir) {
@@ -767,7 +772,7 @@ __device__ __forceinline__ double grad_mag(const GradGeom &gg, double c, double 
 }
 
 // mtanh profile (fusion_kernel.py:380-389) with the two per-equilibrium divisors pre-inverted
-// (correctly rounded Markstein division == the IEEE quotient)
+// (Markstein division, see gsb_internal.cuh)
 struct MtanhK {
   double top, width, half_h, alpha, inv_top, inv_width;
 };
@@ -874,7 +879,9 @@ k_picard_resident(const __grid_constant__ RPlan plan, const __grid_constant__ Pi
   }
 
   // static striding (a dynamic work queue was measured 10-25 % SLOWER: see profiles/r1_v5_summary.md)
-  for (int b = blockIdx.x; b < a.batch; b += gridDim.x) {
+  const int n_work = a.order ? min(*a.n_order, a.batch) : a.batch;
+  for (int wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
+    const int b = a.order ? a.order[wi] : wi;
     const double *bc = a.bc + (size_t)b * n;
     const double ipb = a.ip[b];
     double pp[4], pf[4];
@@ -1356,6 +1363,121 @@ k_picard_resident(const __grid_constant__ RPlan plan, const __grid_constant__ Pi
 #undef GSB_SLOT_LOOP_END
 }
 
+// ---------------------------------------------------------------------------- free-boundary outer loop
+// fb_summary rows: [outer_iterations, final_diff, inner Picard iterations summed over the outer iterations, converged]
+__global__ void k_fb_init(int *__restrict__ mask, int *__restrict__ order, int *__restrict__ n_order,
+                          double *__restrict__ fbsum, int batch) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b == 0) *n_order = batch;
+  if (b >= batch) return;
+  mask[b] = 1;
+  order[b] = b;
+  fbsum[4 * b] = 0.0;
+  fbsum[4 * b + 1] = INFINITY;
+  fbsum[4 * b + 2] = 0.0;
+  fbsum[4 * b + 3] = 0.0;
+}
+
+// index of wall point (iz, ir) in the C-order ring enumeration of wall_coord() (gsb_green.cu)
+__device__ __forceinline__ int wall_index(int nz, int nr, int iz, int ir) {
+  if (iz == 0) return ir;
+  if (iz == nz - 1) return nr + 2 * (nz - 2) + ir;
+  return nr + 2 * (iz - 1) + (ir ? 1 : 0);
+}
+
+// wall ring of psi <- ext ring (+ plasma wall flux); old <- psi
+__global__ void __launch_bounds__(256)
+k_fb_prepare(double *__restrict__ psi, const double *__restrict__ ext, const double *__restrict__ wall,
+             double *__restrict__ old, size_t n, int nz, int nr, int nwall, const int *__restrict__ mask) {
+  const int b = blockIdx.y;
+  if (!mask[b]) return;
+  double *f = psi + (size_t)b * n;
+  const double *e = ext + (size_t)b * n;
+  double *o = old + (size_t)b * n;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int iz = (int)(i / nr), ir = (int)(i - (size_t)iz * nr);
+    double v = f[i];
+    if (iz == 0 || ir == 0 || iz == nz - 1 || ir == nr - 1) {
+      v = e[i];
+      if (wall) v = dadd(v, wall[(size_t)b * nwall + wall_index(nz, nr, iz, ir)]);
+      f[i] = v;
+    }
+    o[i] = v;
+  }
+}
+
+// partial max |psi - old| (NaN wins like np.max)
+__global__ void __launch_bounds__(256)
+k_fb_diff(const double *__restrict__ psi, const double *__restrict__ old, size_t n, double *__restrict__ part,
+          const int *__restrict__ mask) {
+  __shared__ double sh[32];
+  const int b = blockIdx.y, P = gridDim.x, p = blockIdx.x;
+  if (!mask[b]) return;
+  const size_t i0 = n * p / P, i1 = n * (p + 1) / P;
+  const double *f = psi + (size_t)b * n, *o = old + (size_t)b * n;
+  double m = 0.0;
+  int bad = 0;
+  for (size_t i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+    const double d = fabs(dsub(f[i], o[i]));
+    if (d != d) bad = 1;
+    m = fmax(m, d);
+  }
+  const int anybad = __syncthreads_or(bad);
+  m = block_max(m, sh);
+  if (threadIdx.x == 0) {
+    part[((size_t)b * kPT + p) * 2] = m;
+    part[((size_t)b * kPT + p) * 2 + 1] = anybad ? 1.0 : 0.0;
+  }
+}
+
+// One CTA: per-equilibrium outer-loop decision, then an ORDERED compaction of the still-active equilibria
+// (deterministic work list -> deterministic CTA assignment in the next resident launch).
+__global__ void __launch_bounds__(1024)
+k_fb_decide(const double *__restrict__ part, int P, double tol, int outer, const double *__restrict__ summary,
+            double *__restrict__ fbsum, int *__restrict__ mask, int *__restrict__ order, int *__restrict__ n_order,
+            int batch) {
+  __shared__ int wsum[32];
+  __shared__ int base;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) base = 0;
+  __syncthreads();
+  for (int b0 = 0; b0 < batch; b0 += blockDim.x) {
+    const int b = b0 + tid;
+    int keep = 0;
+    if (b < batch && mask[b]) {
+      double m = 0.0;
+      bool bad = false;
+      for (int q = 0; q < P; ++q) {
+        m = fmax(m, part[((size_t)b * kPT + q) * 2]);
+        bad = bad || part[((size_t)b * kPT + q) * 2 + 1] != 0.0;
+      }
+      const double diff = bad ? NAN : m;
+      fbsum[4 * b] = (double)(outer + 1);
+      fbsum[4 * b + 1] = diff;
+      fbsum[4 * b + 2] += summary[(size_t)b * 16];  // Picard iterations of this outer iteration
+      const bool conv = diff < tol;
+      fbsum[4 * b + 3] = conv ? 1.0 : 0.0;
+      keep = conv ? 0 : 1;
+      mask[b] = keep;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    const int pos_in_warp = __popc(bal & ((1u << lane) - 1));
+    if (lane == 0) wsum[warp] = __popc(bal);
+    __syncthreads();
+    int off = base;
+    for (int w = 0; w < warp; ++w) off += wsum[w];
+    if (keep) order[off + pos_in_warp] = b;
+    __syncthreads();
+    if (tid == 0) {
+      int t = 0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += wsum[w];
+      base += t;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) *n_order = base;
+}
+
 }  // namespace gsb
 
 using namespace gsb;
@@ -1537,7 +1659,7 @@ int picard_phase_read(long long *out64, int reset) {
 static int picard_resident_launch(gsb_ctx *ctx, const gsb_picard_params *p, double *psi_dev, const double *bc_dev,
                                   const double *ip_dev, const double *prof_dev, double *jphi_dev,
                                   double *summary_dev, double *hist_dev, double *gs_hist_dev, int batch,
-                                  cudaStream_t st) {
+                                  const int *order_dev, const int *n_order_dev, cudaStream_t st) {
   constexpr int kScratch = 96;
   RPlan plan;
   if (!build_rplan(ctx, 0, kScratch, &plan) || plan.nlev < 2) return GSB_ESTATE;
@@ -1599,11 +1721,9 @@ static int picard_resident_launch(gsb_ctx *ctx, const gsb_picard_params *p, doub
   a.prof = to_dev(p->prof);
   a.scratch_off = plan.pool_doubles + res_stage_doubles(plan.nlev);
   a.tplane_off = c1.x_off;
-  static bool attr_set = false;
-  if (!attr_set) {
-    GSB_CUDA(cudaFuncSetAttribute(k_picard_resident, cudaFuncAttributeMaxDynamicSharedMemorySize, kResSmemMax));
-    attr_set = true;
-  }
+  a.order = order_dev;
+  a.n_order = n_order_dev;
+  GSB_SMEM_OPT_IN(k_picard_resident, kResSmemMax);
   const size_t smem = (size_t)(a.scratch_off + kScratch) * sizeof(double);
   k_picard_resident<<<grid, kResThreads, smem, st>>>(plan, a);
   GSB_LAUNCH_CHECK();
@@ -1702,9 +1822,13 @@ int gsb_b_field(gsb_ctx *ctx, const double *psi_dev, double *br_dev, double *bz_
 
 int gsb_picard_last_launched_iterations(gsb_ctx *ctx) { return ctx ? ctx->picard_last_iters : 0; }
 
-int gsb_picard_solve(gsb_ctx *ctx, const gsb_picard_params *p, double *psi_dev, const double *bc_dev,
-                     const double *ip_dev, const double *prof_dev, double *jphi_dev, double *summary_dev,
-                     double *hist_dev, double *gs_hist_dev, int batch, void *stream) {
+// The batched Picard solve behind gsb_picard_solve and the free-boundary outer loop.  mask_dev / order_dev /
+// n_order_dev (all NULL, or all set and consistent: mask[b] != 0 <=> b is one of the first *n_order entries of
+// order) restrict the solve to a subset of the batch; everything else is left untouched.
+static int picard_solve_impl(gsb_ctx *ctx, const gsb_picard_params *p, double *psi_dev, const double *bc_dev,
+                             const double *ip_dev, const double *prof_dev, double *jphi_dev, double *summary_dev,
+                             double *hist_dev, double *gs_hist_dev, int batch, const int *mask_dev,
+                             const int *order_dev, const int *n_order_dev, void *stream) {
   GSB_REQUIRE(ctx && p && psi_dev && bc_dev && ip_dev && jphi_dev && summary_dev, "gsb_picard_solve: NULL argument");
   GSB_REQUIRE(batch >= 1 && batch <= ctx->batch_cap, "gsb_picard_solve: batch outside [1, batch_cap]");
   GSB_REQUIRE(p->max_iterations >= 1, "gsb_picard_solve: max_iterations must be >= 1");
@@ -1728,13 +1852,13 @@ int gsb_picard_solve(gsb_ctx *ctx, const gsb_picard_params *p, double *psi_dev, 
   const GradGeom gg = make_grad_geom(ctx->dz, ctx->dr);
   if (p->method == 0 && !std::getenv("GSB_PICARD_STREAMING")) {
     rc = picard_resident_launch(ctx, p, psi_dev, bc_dev, ip_dev, prof_dev, jphi_dev, summary_dev, hist_dev,
-                                gs_hist_dev, batch, st);
+                                gs_hist_dev, batch, order_dev, n_order_dev, st);
     if (rc != GSB_ESTATE) return rc;  // GSB_ESTATE: one equilibrium does not fit an SM -> streaming path
   }
   const int copy_blocks = (int)std::min<size_t>((n + 255) / 256, 64);
   const ProfileDev prof = to_dev(p->prof);
 
-  k_picard_init<<<(batch + 127) / 128, 128, 0, st>>>(s, batch, p->seed ? 2 : 0, ip_dev, p->seed);
+  k_picard_init<<<(batch + 127) / 128, 128, 0, st>>>(s, batch, p->seed ? 2 : 0, ip_dev, p->seed, mask_dev);
   GSB_LAUNCH_CHECK();
   rc = ring_save_launch(bc_dev, n, w->ring, nz, nr, batch, st);
   if (rc) return rc;
@@ -1806,9 +1930,86 @@ int gsb_picard_solve(gsb_ctx *ctx, const gsb_picard_params *p, double *psi_dev, 
     }
   }
   ctx->picard_last_iters = k;
-  k_finalize<<<dim3(copy_blocks, batch), 256, 0, st>>>(bufs, s, n, summary_dev, batch);
+  k_finalize<<<dim3(copy_blocks, batch), 256, 0, st>>>(bufs, s, n, summary_dev, batch, mask_dev);
   GSB_LAUNCH_CHECK();
   return GSB_OK;
+}
+
+int gsb_picard_solve(gsb_ctx *ctx, const gsb_picard_params *p, double *psi_dev, const double *bc_dev,
+                     const double *ip_dev, const double *prof_dev, double *jphi_dev, double *summary_dev,
+                     double *hist_dev, double *gs_hist_dev, int batch, void *stream) {
+  return picard_solve_impl(ctx, p, psi_dev, bc_dev, ip_dev, prof_dev, jphi_dev, summary_dev, hist_dev, gs_hist_dev,
+                           batch, nullptr, nullptr, nullptr, stream);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Batched free-boundary outer loop (solve_free_boundary, fusion_kernel_free_boundary.py:623-739) on device:
+//   per outer iteration, for every equilibrium that has not converged yet:
+//     wall ring of Psi <- coil flux ring [+ plasma wall flux M @ (J dA)]      (:652-655; lane C :498)
+//     Psi_old <- Psi                                                          (:658)
+//     warm-started, re-seeded Picard solve with that boundary map            (:659-662)
+//     diff = max |Psi - Psi_old|; stop this equilibrium when diff < tol       (:708-711)
+// The host only reads one counter per OUTER iteration.
+// ---------------------------------------------------------------------------------------------------------
+int gsb_free_boundary_solve(gsb_ctx *ctx, const gsb_picard_params *p, const gsb_free_boundary_params *fb,
+                            double *psi_dev, const double *psi_ext_dev, const double *wall_m_dev,
+                            const double *ip_dev, const double *prof_dev, double *jphi_dev, double *summary_dev,
+                            double *fb_summary_dev, int batch, void *stream) {
+  GSB_REQUIRE(ctx && p && fb && psi_dev && psi_ext_dev && ip_dev && jphi_dev && summary_dev && fb_summary_dev,
+              "gsb_free_boundary_solve: NULL argument");
+  GSB_REQUIRE(batch >= 1 && batch <= ctx->batch_cap && batch <= 65535, "gsb_free_boundary_solve: batch outside [1, min(batch_cap, 65535)]");
+  GSB_REQUIRE(fb->max_outer_iter >= 1, "max_outer_iter must be >= 1.");
+  GSB_REQUIRE(std::isfinite(fb->tol) && fb->tol >= 0.0, "tol must be finite and >= 0.");
+  GSB_REQUIRE(ctx->nz >= 3 && ctx->nr >= 3, "gsb_free_boundary_solve: grid has no interior");
+  GSB_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n = ctx->n;
+  const int nz = ctx->nz, nr = ctx->nr, nw = ctx->n_wall;
+  // workspace: previous iterate, masks / work list, reduction partials, plasma wall flux
+  double *old = nullptr, *part = nullptr, *wall = nullptr;
+  int *ints = nullptr;
+  GSB_CUDA(cudaMallocAsync(&old, (size_t)batch * n * sizeof(double), st));
+  GSB_CUDA(cudaMallocAsync(&part, (size_t)batch * kPT * 2 * sizeof(double), st));
+  GSB_CUDA(cudaMallocAsync(&ints, ((size_t)2 * batch + 2) * sizeof(int), st));
+  if (wall_m_dev) GSB_CUDA(cudaMallocAsync(&wall, (size_t)batch * nw * sizeof(double), st));
+  int *mask = ints, *order = ints + batch, *n_order = ints + 2 * batch;
+  const int P = partials_for(nz, nr);
+  const int blocks = (int)std::min<size_t>((n + 255) / 256, 64);
+  int rc = GSB_OK;
+  auto cleanup = [&]() {
+    cudaFreeAsync(old, st);
+    cudaFreeAsync(part, st);
+    cudaFreeAsync(ints, st);
+    if (wall) cudaFreeAsync(wall, st);
+  };
+  k_fb_init<<<(batch + 255) / 256, 256, 0, st>>>(mask, order, n_order, fb_summary_dev, batch);
+  GSB_LAUNCH_CHECK();
+  const double dA = ctx->dr * ctx->dz;
+  int outer = 0;
+  for (; outer < fb->max_outer_iter; ++outer) {
+    const bool with_wall = wall_m_dev && (outer > 0 || fb->warm_j);
+    if (with_wall) {
+      rc = gsb_wall_flux(ctx, wall_m_dev, jphi_dev, dA, wall, batch, stream);
+      if (rc) break;
+    }
+    k_fb_prepare<<<dim3(blocks, batch), 256, 0, st>>>(psi_dev, psi_ext_dev, with_wall ? wall : nullptr, old, n, nz, nr, nw, mask);
+    GSB_LAUNCH_CHECK();
+    rc = picard_solve_impl(ctx, p, psi_dev, psi_dev /* the ring of psi IS the boundary map */, ip_dev, prof_dev, jphi_dev,
+                           summary_dev, nullptr, nullptr, batch, mask, order, n_order, stream);
+    if (rc) break;
+    k_fb_diff<<<dim3(P, batch), 256, 0, st>>>(psi_dev, old, n, part, mask);
+    GSB_LAUNCH_CHECK();
+    k_fb_decide<<<1, 1024, 0, st>>>(part, P, fb->tol, outer, summary_dev, fb_summary_dev, mask, order, n_order, batch);
+    GSB_LAUNCH_CHECK();
+    GSB_CUDA(cudaMemcpyAsync(ctx->h_counter, n_order, sizeof(int), cudaMemcpyDeviceToHost, st));
+    GSB_CUDA(cudaStreamSynchronize(st));
+    if (ctx->h_counter[0] == 0) {
+      ++outer;
+      break;
+    }
+  }
+  cleanup();
+  return rc;
 }
 
 }  // extern "C"

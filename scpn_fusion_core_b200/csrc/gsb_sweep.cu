@@ -122,7 +122,7 @@ __device__ __forceinline__ void sweep_warp_body(const SweepArgs &a, double *ring
           acc = dadd(acc, dmul(a_ns, N[t]));
           acc = dsub(acc, F[t]);
           const double qq = __dmul_rn(acc, inv_a_c);
-          const double gs = __fma_rn(__fma_rn(-a_c, qq, acc), inv_a_c, qq);  // acc / a_c, correctly rounded
+          const double gs = __fma_rn(__fma_rn(-a_c, qq, acc), inv_a_c, qq);  // acc / a_c (Markstein sequence, gsb_internal.cuh)
           V[t] = dadd(dmul(omw, O[t]), dmul(omega, gs));
         }
 #pragma unroll
@@ -246,13 +246,9 @@ int sweep_fused_launch(const LevelGeom &g, const double *in, size_t istride, dou
   a.active = active;
   const size_t smem = sweep_smem_bytes(nst);
   const dim3 grd((ns + kSwWPC - 1) / kSwWPC, nb, batch), blk(32 * kSwWPC, 1, 1);
-  static bool attr_set = false;
-  if (!attr_set) {
-    GSB_CUDA(cudaFuncSetAttribute(k_sweep_warp<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem_bytes(2)));
-    GSB_CUDA(cudaFuncSetAttribute(k_sweep_warp<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem_bytes(4)));
-    GSB_CUDA(cudaFuncSetAttribute(k_sweep_warp<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem_bytes(6)));
-    attr_set = true;
-  }
+  GSB_SMEM_OPT_IN(k_sweep_warp<2>, sweep_smem_bytes(2));
+  GSB_SMEM_OPT_IN(k_sweep_warp<4>, sweep_smem_bytes(4));
+  GSB_SMEM_OPT_IN(k_sweep_warp<6>, sweep_smem_bytes(6));
   if (nst == 2)
     k_sweep_warp<2><<<grd, blk, smem, st>>>(a);
   else if (nst == 4)

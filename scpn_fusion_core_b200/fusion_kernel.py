@@ -148,6 +148,8 @@ class _GridMixin:
         self.dR = float(self.R[1] - self.R[0])
         self.dZ = float(self.Z[1] - self.Z[0])
         self.RR, self.ZZ = np.meshgrid(self.R, self.Z)
+        for stale in ("_green_cache", "_wall_m_cache", "_fb_ext"):  # device tables of the previous grid
+            self.__dict__.pop(stale, None)
         self.profile_mode = "l-mode"
         self.ped_params_p = {"ped_top": 0.92, "ped_width": 0.05, "ped_height": 1.0, "core_alpha": 0.3}
         self.ped_params_ff = dict(self.ped_params_p)
@@ -395,10 +397,17 @@ class FusionKernel(FreeBoundaryMixin, _GridMixin):
         gs_hist = [float(v) for v in out["gs_hist"][0][:n_hist]]
         self._last_topology = s[6:12].copy()
         self.compute_b_field()
+        if gs_hist:
+            gs_final, gs_best = gs_hist[-1], float(s[4])
+        else:
+            # diverged in the very first iteration: the reference reports the GS RMS of the reverted state against
+            # the last source it formed (fusion_kernel_newton_solver.py:584-590, `final_source`)
+            mu0 = float(self.cfg["physics"]["vacuum_permeability"])
+            gs_final = gs_best = self._compute_gs_residual_rms(-mu0 * self.RR * self.J_phi)
         return {"psi": self.Psi, "converged": bool(s[1]), "iterations": iters, "residual": float(s[2]),
                 "residual_history": hist,
-                "gs_residual": gs_hist[-1] if gs_hist else float("inf"),
-                "gs_residual_best": float(s[4]) if gs_hist else float("inf"),
+                "gs_residual": gs_final,
+                "gs_residual_best": gs_best,
                 "gs_residual_history": gs_hist, "wall_time_s": time.time() - t0, "solver_method": method}
 
     # -- post-processing -----------------------------------------------------------------------
@@ -541,12 +550,35 @@ class BatchedFusionKernel(_GridMixin):
         w = (mu0 * np.asarray(coil_currents, dtype=np.float64)) / (2.0 * np.pi)
         return self._coil_flux_dev(pos, w, 0)
 
+    def pinned_outputs(self, batch: int, fields=("psi", "j_phi")) -> dict:
+        """Pinned host tensors (B, nz, nr) for ``solve(..., out=...)`` / ``solve_free_boundary(..., out=...)``: the
+        flux maps then reach the host with one asynchronous DMA each instead of a pageable staging copy."""
+        torch = D.torch_mod()
+        return {k: torch.empty((batch, self.NZ, self.NR), dtype=torch.float64).pin_memory() for k in fields}
+
+    def _fields_to_host(self, res: dict, dev: dict, to_host: bool, out: dict | None) -> None:
+        for name in ("psi", "j_phi"):
+            if not to_host:
+                res[name] = dev[name]
+            elif out is not None:
+                if name in out:  # fields the caller did not ask for stay on the device
+                    out[name].copy_(dev[name], non_blocking=True)
+                    res[name] = out[name].numpy()
+                else:
+                    res[name] = dev[name]
+            else:
+                res[name] = dev[name].cpu().numpy()
+        if to_host and out is not None:
+            D.torch_mod().cuda.current_stream().synchronize()
+
     def solve(self, coil_currents=None, plasma_current=None, ped_p=None, ped_ff=None, *, batch: int | None = None,
-              to_host: bool = True, want_history: bool = False) -> dict[str, Any]:
+              to_host: bool = True, want_history: bool = False, out: dict | None = None) -> dict[str, Any]:
         """Solve the batch; returns arrays with a leading batch axis.
 
         coil_currents (B, n_coils) | None (config currents), plasma_current (B,) | None,
         ped_p / ped_ff (B, 4) | None: [ped_top, ped_width, ped_height, core_alpha].
+        ``out`` = ``pinned_outputs(B)`` (or a subset of its keys): those fields are copied into the given pinned
+        host tensors and returned as NumPy views of them; fields not in ``out`` stay on the device.
         """
         params = self._picard_params()
         base_i = np.array([c["current"] for c in self.cfg["coils"]], dtype=np.float64)
@@ -560,13 +592,7 @@ class BatchedFusionKernel(_GridMixin):
             else np.asarray(plasma_current, dtype=np.float64).reshape(B)
         if np.any(np.abs(ip) < 1e-12):
             raise NotImplementedError("zero plasma current samples: use FusionKernel.calculate_vacuum_field")
-        ped = None
-        if ped_p is not None or ped_ff is not None:
-            dp = np.array([self.ped_params_p[k] for k in _PED_KEYS])
-            df = np.array([self.ped_params_ff[k] for k in _PED_KEYS])
-            pp = np.tile(dp, (B, 1)) if ped_p is None else np.asarray(ped_p, dtype=np.float64).reshape(B, 4)
-            pf = np.tile(df, (B, 1)) if ped_ff is None else np.asarray(ped_ff, dtype=np.float64).reshape(B, 4)
-            ped = np.concatenate([pp, pf], axis=1)
+        ped = self._ped_rows(B, ped_p, ped_ff)
         t0 = time.time()
         mu0 = self.cfg["physics"].get("vacuum_permeability", 1.0)
         w = (mu0 * cc) / (2.0 * np.pi)
@@ -575,8 +601,7 @@ class BatchedFusionKernel(_GridMixin):
                                 want_history=want_history)
         s = dev["summary"].cpu().numpy()
         res = self.unpack_summary(s)
-        res["psi"] = dev["psi"].cpu().numpy() if to_host else dev["psi"]
-        res["j_phi"] = dev["j_phi"].cpu().numpy() if to_host else dev["j_phi"]
+        self._fields_to_host(res, dev, to_host, out)
         res["wall_time_s"] = time.time() - t0
         if want_history:
             res["residual_history"] = dev["hist"].cpu().numpy()
@@ -604,6 +629,123 @@ class BatchedFusionKernel(_GridMixin):
             "xpoint_R": np.where(s[:, 13] > 0, self.R[s[:, 11].astype(np.int64)], 0.0),
             "xpoint_Z": np.where(s[:, 13] > 0, self.Z[s[:, 10].astype(np.int64)], 0.0),
         }
+
+    # -- batched free boundary (a17 + a18) -------------------------------------------------------------
+    def wall_response_matrix(self, mu0: float = _MU0_SI):
+        """Lane-C von Hagenow matrix M[N_wall, N_interior] on the device (build_response_matrix,
+        jax_free_boundary_predictive.py:183-211), cached per mu0: geometry only."""
+        cache = self.__dict__.setdefault("_wall_m_cache", {})
+        key = float(mu0)
+        if key not in cache:
+            ctx = self._context(1)
+            n_wall = 2 * self.NR + 2 * (self.NZ - 2)
+            n_int = (self.NZ - 2) * (self.NR - 2)
+            m = D.empty((n_wall, n_int), self.device)
+            _lib.check(ctx.lib.gsb_wall_matrix(ctx.handle, key, D.ptr(m), D.stream_ptr()), "gsb_wall_matrix")
+            cache[key] = m
+        return cache[key]
+
+    def _ped_rows(self, B: int, ped_p, ped_ff):
+        if ped_p is None and ped_ff is None:
+            return None
+        dp = np.array([self.ped_params_p[k] for k in _PED_KEYS])
+        df = np.array([self.ped_params_ff[k] for k in _PED_KEYS])
+        pp = np.tile(dp, (B, 1)) if ped_p is None else np.asarray(ped_p, dtype=np.float64).reshape(B, 4)
+        pf = np.tile(df, (B, 1)) if ped_ff is None else np.asarray(ped_ff, dtype=np.float64).reshape(B, 4)
+        return np.concatenate([pp, pf], axis=1)
+
+    def solve_free_boundary(self, coil_currents=None, plasma_current=None, ped_p=None, ped_ff=None, *, turns=None,
+                            max_outer_iter: int = 20, tol: float = 1e-4, plasma_wall: bool = False,
+                            wall_mu0: float = _MU0_SI, psi0=None, batch: int | None = None, to_host: bool = True,
+                            out: dict | None = None) -> dict[str, Any]:
+        """``FusionKernel.solve_free_boundary(coils, max_outer_iter, tol)`` (fusion_kernel_free_boundary.py:623-739,
+        ``optimize_shape=False``) for B independent equilibria in one device-resident outer loop.
+
+        coil_currents (B, n_coils) | None (config currents; then give ``batch``), turns (n_coils,) | None (config
+        ``turns``, default 1), plasma_current (B,) | None, ped_p / ped_ff (B, 4) | None.  ``plasma_wall=True`` adds
+        the plasma's own wall flux M @ (J_phi dA) (lane C, jax_free_boundary_predictive.py:443-498) from the second
+        outer iteration on, as one FP64 tensor-core GEMM over the batch per outer iteration.  ``psi0`` (B, nz, nr)
+        is the starting flux (default zeros, the state of a freshly constructed kernel).  ``out`` may carry pinned
+        host tensors (``pinned_outputs``) to receive the fields without a pageable staging copy (see ``solve``).
+        Returns per-equilibrium arrays: outer_iterations, final_diff, inner_iterations (sum over the outer
+        iterations), fb_converged, plus the keys of ``solve`` for the last inner solve.
+        """
+        if max_outer_iter < 1:
+            raise ValueError("max_outer_iter must be >= 1.")
+        if not np.isfinite(tol) or tol < 0.0:
+            raise ValueError("tol must be finite and >= 0.")
+        coils = self.cfg["coils"]
+        base_i = np.array([c["current"] for c in coils], dtype=np.float64)
+        if coil_currents is None:
+            if batch is None:
+                raise ValueError("give coil_currents or batch")
+            coil_currents = np.tile(base_i, (batch, 1))
+        cc = np.ascontiguousarray(np.asarray(coil_currents, dtype=np.float64))
+        B = cc.shape[0]
+        tr = np.array([int(c.get("turns", 1)) for c in coils], dtype=np.float64) if turns is None \
+            else np.asarray(turns, dtype=np.float64).reshape(len(coils))
+        ip = np.full(B, float(self.cfg["physics"]["plasma_current_target"])) if plasma_current is None \
+            else np.asarray(plasma_current, dtype=np.float64).reshape(B)
+        if np.any(np.abs(ip) < 1e-12):
+            raise NotImplementedError("zero plasma current samples: use FusionKernel.solve_free_boundary")
+        ped = self._ped_rows(B, ped_p, ped_ff)
+        t0 = time.time()
+        w = cc * tr[None, :]  # I * turns (fusion_kernel_free_boundary.py:88-92)
+        psi_in = None if psi0 is None else D.to_device(np.asarray(psi0, dtype=np.float64).reshape(B, self.NZ, self.NR),
+                                                       self.device)
+        dev = self.solve_free_boundary_device(D.to_device(w, self.device), D.to_device(ip, self.device),
+                                              None if ped is None else D.to_device(ped, self.device),
+                                              max_outer_iter=max_outer_iter, tol=tol, plasma_wall=plasma_wall,
+                                              wall_mu0=wall_mu0, psi_out=psi_in, warm=psi0 is not None)
+        res = self.unpack_summary(dev["summary"].cpu().numpy())
+        fb = dev["fb_summary"].cpu().numpy()
+        res.update({"outer_iterations": fb[:, 0].astype(np.int64), "final_diff": fb[:, 1],
+                    "inner_iterations": fb[:, 2].astype(np.int64), "fb_converged": fb[:, 3] > 0.5})
+        self._fields_to_host(res, dev, to_host, out)
+        res["wall_time_s"] = time.time() - t0
+        return res
+
+    def solve_free_boundary_device(self, w_dev, ip_dev, ped_dev=None, *, max_outer_iter: int = 20, tol: float = 1e-4,
+                                   plasma_wall: bool = False, wall_mu0: float = _MU0_SI, psi_out=None, jphi_out=None,
+                                   warm: bool = False, events=None) -> dict[str, Any]:
+        """Device-resident batched free-boundary solve (gsb_free_boundary_solve): w_dev (B, n_coils) = I*turns,
+        ip_dev (B,), ped_dev (B, 8) | None - CUDA float64 tensors.  ``psi_out`` is the flux buffer (its content is
+        the starting flux when ``warm``, otherwise it is zeroed).  Returns device tensors psi, j_phi, psi_ext,
+        summary (B, 16), fb_summary (B, 4)."""
+        params = self._picard_params()
+        B = int(w_dev.shape[0])
+        ctx = self._context(B)
+        pos = [(c["r"], c["z"]) for c in self.cfg["coils"]]
+        nc = len(pos)
+        st = D.stream_ptr()
+        ext = self.__dict__.get("_fb_ext")
+        if ext is None or ext.shape[0] != B:
+            ext = self._fb_ext = D.empty((B, self.NZ, self.NR), self.device)
+        if nc:
+            g = self._green_table(pos, 1)
+            _lib.check(ctx.lib.gsb_coil_flux(ctx.handle, D.ptr(g), D.ptr(w_dev), nc, 1, D.ptr(ext), B, st), "gsb_coil_flux")
+        else:
+            ext.zero_()
+        psi = psi_out if psi_out is not None else D.empty((B, self.NZ, self.NR), self.device)
+        jphi = jphi_out if jphi_out is not None else D.empty((B, self.NZ, self.NR), self.device)
+        if not warm:
+            psi.zero_()
+            jphi.zero_()
+        summ = D.empty((B, 16), self.device)
+        fbs = D.empty((B, 4), self.device)
+        m = self.wall_response_matrix(wall_mu0) if plasma_wall else None
+        fb = _lib.gsb_free_boundary_params()
+        fb.max_outer_iter, fb.tol, fb.warm_j = int(max_outer_iter), float(tol), 0
+        null = ctypes.c_void_p()
+        if events is not None:
+            events[0].record()
+        _lib.check(ctx.lib.gsb_free_boundary_solve(ctx.handle, ctypes.byref(params), ctypes.byref(fb), D.ptr(psi), D.ptr(ext),
+                                                   null if m is None else D.ptr(m), D.ptr(ip_dev),
+                                                   null if ped_dev is None else D.ptr(ped_dev), D.ptr(jphi), D.ptr(summ),
+                                                   D.ptr(fbs), B, st), "gsb_free_boundary_solve")
+        if events is not None:
+            events[1].record()
+        return {"psi": psi, "j_phi": jphi, "psi_ext": ext, "summary": summ, "fb_summary": fbs}
 
     def solve_device(self, w_dev, ip_dev, ped_dev=None, *, want_history: bool = False, psi_out=None,
                      jphi_out=None, events=None) -> dict[str, Any]:

@@ -140,7 +140,7 @@ class CudaSlabOps:
         return t.cpu().numpy()
 
     def _context(self, L: SlabLevel):
-        key = (L.nz, L.nr, L.rows_loc, L.dr, L.dz)
+        key = (L.nz, L.nr, L.rows_loc, L.dr, L.dz, np.ascontiguousarray(L.r_row, dtype=np.float64).tobytes())
         if key not in self._ctx:
             self._ctx[key] = self.D.Context(L.rows_loc, L.nr, L.r_row, None, L.dr, L.dz, 1, self.device)
         return self._ctx[key]
@@ -202,7 +202,7 @@ class CudaSlabOps:
         """The replicated tail of the V-cycle on the gathered level (zero initial guess): one gsb_vcycle
         call on a cached context of that level's geometry (multigrid_solve.py:252-335 from level `G`)."""
         D = self.D
-        key = ("coarse", G["nz"], G["nr"], G["dr"], G["dz"])
+        key = ("coarse", G["nz"], G["nr"], G["dr"], G["dz"], np.ascontiguousarray(G["r_row"], dtype=np.float64).tobytes())
         ctx = self._ctx.get(key)
         if ctx is None:
             ctx = self._ctx[key] = D.Context(G["nz"], G["nr"], G["r_row"], None, G["dr"], G["dz"], 1, self.device)
@@ -223,11 +223,17 @@ class SlabComm:
         self.backend = dist.get_backend(group) if world > 1 else "none"
         self.bytes_sent = 0
         self.messages = 0
+        self.peer = None
+        # bumped whenever the peer-memory transport is (re)created or torn down: a SlabMultigrid that cached raw
+        # inbox / flag pointers (native descriptors, a captured graph) for an older generation must rebuild them
+        self.peer_generation = 0
 
     def enable_peer_halo(self, device: int, max_doubles: int) -> bool:
         """Exchange halos over NVLink peer memory with libgsb200's own push/recv kernels instead of NCCL
         point-to-point launches (one process per GPU, buffers shared through CUDA IPC).  Collective:
         every rank of the group must call it.  Returns False (and keeps NCCL) if IPC is unavailable."""
+        if getattr(self, "peer", None) is not None:
+            self.disable_peer_halo()
         self.peer = None
         if self.world == 1:
             return False
@@ -258,15 +264,23 @@ class SlabComm:
         flag = torch.tensor([ok], dtype=torch.int32, device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
         if int(flag.item()) == 0:
+            # some rank could not map a neighbour: unmap what this rank opened and release its own block
+            for nb in peers.values():
+                lib.gsb_ipc_close(C.c_void_p(nb["flags"]))
+            dist.barrier(group=self.group)  # nobody still maps this rank's block when it is freed
+            lib.gsb_ipc_free(base)
             return False
         own = {"flags": base.value, "inbox_up": base.value + 256, "inbox_dn": base.value + 256 + inbox_bytes}
         self.peer = {"own": own, "peers": peers, "counters": torch.zeros(4, dtype=torch.int32, device=dev),
                      "epochs": torch.zeros(4, dtype=torch.int64, device=dev), "cap": max_doubles, "lib": lib}
+        self.peer_generation += 1
         return True
 
     def disable_peer_halo(self) -> None:
         """Unmap the neighbours' IPC blocks and free this rank's (collective in spirit: call it on every rank
-        once no exchange is in flight; NCCL point-to-point exchanges take over again)."""
+        once no exchange is in flight; NCCL point-to-point exchanges take over again).  Solvers that cached
+        pointers into these blocks (native level descriptors, captured graphs) see the new
+        ``peer_generation`` at their next ``solve()`` and rebuild their state."""
         P = getattr(self, "peer", None)
         if P is None:
             return
@@ -278,6 +292,7 @@ class SlabComm:
             P["lib"].gsb_ipc_close(C.c_void_p(nb["flags"]))
         P["lib"].gsb_ipc_free(C.c_void_p(P["own"]["flags"]))
         self.peer = None
+        self.peer_generation += 1
 
     def _exchange_peer(self, x, L: SlabLevel, k: int) -> None:
         import ctypes as C
@@ -534,9 +549,16 @@ class SlabMultigrid:
         # persistent level-0 buffers: a captured graph (below) refers to their addresses, so repeated
         # solves on the same SlabMultigrid reuse one graph
         st = self._state
+        gen = getattr(comm, "peer_generation", 0)
+        if st and st.get("peer_generation") != gen:
+            # the halo transport changed under us (enable/disable_peer_halo): descriptors and graphs built for
+            # the old inboxes / flags would touch freed or unmapped memory - drop them
+            st.clear()
+            self._native = None
         if not st:
             st["f"], st["bc"], st["x"] = (ops.zeros((L.rows_loc, L.nr)) for _ in range(3))
             st["graph"] = None
+            st["peer_generation"] = gen
             st["native"] = self._native_setup(st["x"], st["f"])
         f, bc = st["f"], st["bc"]
         f.zero_()

@@ -545,6 +545,23 @@ def gen_hpc():
     _save("hpc_solver", **out)
 
 
+def gen_mg_4097():
+    """BASELINE configs[4] / SURVEY.md 8d config 5: the reference's multigrid_solve on the 4097^2 bench problem
+    (bench_gpu_gs_solver._problem source, psi_bc = 0, tol 1e-8, omega 1.0, 3/3, min_grid 5; 13 levels).  Run once
+    (minutes of NumPy time); the fixture keeps the scalars, sum(psi), a 16-row stripe through the source peak and
+    a 32-strided sample of the whole field."""
+    n = 4097
+    r_axis = np.linspace(4.0, 8.0, n)
+    z_axis = np.linspace(-4.0, 4.0, n)
+    rr, zz = np.meshgrid(r_axis, z_axis)
+    src = -np.exp(-((rr - 6.0) ** 2 + zz ** 2) / 0.5)
+    del rr, zz
+    psi, res, cycles, conv = ref_mg.multigrid_solve(src, np.zeros((n, n)), 4.0, 8.0, -4.0, 4.0, n, n, tol=1e-8,
+                                                   max_cycles=50)
+    _save("mg_solve_4097", meta=np.array([res, cycles, float(conv), float(np.sum(psi))]),
+          stripe_rows=np.array([2040, 2056]), stripe=psi[2040:2056].copy(), strided=psi[::32, ::32].copy())
+
+
 def gen_elliptic():
     tab = json.load(open(os.path.join(REF, "scpn-fusion-rs", "tests", "reference", "reference_elliptic.json")))
     m = np.array([float(x) for x in tab["K"].keys()])
@@ -554,6 +571,7 @@ def gen_elliptic():
 if __name__ == "__main__":
     which = sys.argv[1:] or ["ops", "mg_solve", "bench_smooth", "picard_pieces", "solves",
                              "solve_129_validated", "free_boundary", "free_boundary_shape", "dataset", "eqdsk", "anderson", "solovev", "hpc", "elliptic"]
+    # "mg_4097" is generated on request only (several minutes of NumPy time)
     for w in which:
         print("==", w)
         globals()["gen_" + w]()
