@@ -215,6 +215,11 @@ int gsb_free_boundary_solve(gsb_ctx *ctx, const gsb_picard_params *p, const gsb_
                             const double *ip_dev, const double *prof_dev, double *jphi_dev, double *summary_dev,
                             double *fb_summary_dev, int batch, void *stream);
 
+/* Measurement hook (bench.py roofline): while enabled, gsb_free_boundary_solve brackets every inner Picard solve and
+ * every wall GEMM with CUDA events on the launching stream and accumulates
+ * out4 = {Picard solves: total ms, count; wall GEMMs: total ms, count}.  out4 may be NULL; reset != 0 zeroes the sums. */
+int gsb_timing(gsb_ctx *ctx, int enable, double *out4, int reset);
+
 /* compute_b_field (fusion_kernel.py:450-456): np.gradient + 1/max(R,1e-6). */
 int gsb_b_field(gsb_ctx *ctx, const double *psi_dev, double *br_dev, double *bz_dev, int batch,
                 void *stream);

@@ -13,6 +13,7 @@ import numpy as np
 from . import _lib
 
 _dp = POINTER(c_double)
+_PINNED_STAGE_MAX = 8 << 20
 
 
 def torch_mod():
@@ -39,7 +40,12 @@ def to_device(a, device: int):
     if isinstance(a, torch.Tensor):
         return a.to(device=f"cuda:{device}", dtype=torch.float64).contiguous().clone()
     h = np.ascontiguousarray(np.asarray(a, dtype=np.float64))
-    return torch.from_numpy(h).to(f"cuda:{device}")
+    t = torch.from_numpy(h)
+    if 0 < h.nbytes <= _PINNED_STAGE_MAX:
+        # per-sample parameter arrays (KBs): stage through pinned host memory so the copy is one asynchronous DMA;
+        # large fields go straight from the caller's pageable array (pinning them would cost more than it saves)
+        return t.pin_memory().to(f"cuda:{device}", non_blocking=True)
+    return t.to(f"cuda:{device}")
 
 
 def empty(shape, device: int, dtype=None):

@@ -75,6 +75,7 @@ SIGNATURES = {
     "gsb_picard_solve": (c_int, [c_void_p, POINTER(gsb_picard_params), c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "gsb_picard_last_launched_iterations": (c_int, [c_void_p]),
+    "gsb_timing": (c_int, [c_void_p, c_int, _dp, c_int]),
     "gsb_free_boundary_solve": (c_int, [c_void_p, POINTER(gsb_picard_params), POINTER(gsb_free_boundary_params), c_void_p,
                                         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                         c_void_p]),

@@ -332,6 +332,9 @@ struct gsb_ctx {
   double *mg_bc = nullptr;  // wall ring copy for mg_solve [batch_cap][ring]
   gsb_picard_ws *picard = nullptr;
   int picard_last_iters = 0;
+  // optional per-kernel-class timing of gsb_free_boundary_solve (gsb_timing): CUDA events on the launching stream
+  bool timing = false;
+  double timing_acc[4] = {0, 0, 0, 0};  // inner Picard solves: ms, count; wall GEMMs: ms, count
   // lane-C wall indices
   int n_wall = 0, n_int = 0;
 };

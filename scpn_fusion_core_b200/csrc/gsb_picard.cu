@@ -1985,31 +1985,55 @@ int gsb_free_boundary_solve(gsb_ctx *ctx, const gsb_picard_params *p, const gsb_
   k_fb_init<<<(batch + 255) / 256, 256, 0, st>>>(mask, order, n_order, fb_summary_dev, batch);
   GSB_LAUNCH_CHECK();
   const double dA = ctx->dr * ctx->dz;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  if (ctx->timing)
+    for (auto &e : ev) GSB_CUDA(cudaEventCreate(&e));
   int outer = 0;
   for (; outer < fb->max_outer_iter; ++outer) {
     const bool with_wall = wall_m_dev && (outer > 0 || fb->warm_j);
     if (with_wall) {
+      if (ctx->timing) cudaEventRecord(ev[2], st);
       rc = gsb_wall_flux(ctx, wall_m_dev, jphi_dev, dA, wall, batch, stream);
       if (rc) break;
+      if (ctx->timing) cudaEventRecord(ev[3], st);
     }
     k_fb_prepare<<<dim3(blocks, batch), 256, 0, st>>>(psi_dev, psi_ext_dev, with_wall ? wall : nullptr, old, n, nz, nr, nw, mask);
     GSB_LAUNCH_CHECK();
+    if (ctx->timing) cudaEventRecord(ev[0], st);
     rc = picard_solve_impl(ctx, p, psi_dev, psi_dev /* the ring of psi IS the boundary map */, ip_dev, prof_dev, jphi_dev,
                            summary_dev, nullptr, nullptr, batch, mask, order, n_order, stream);
     if (rc) break;
+    if (ctx->timing) cudaEventRecord(ev[1], st);
     k_fb_diff<<<dim3(P, batch), 256, 0, st>>>(psi_dev, old, n, part, mask);
     GSB_LAUNCH_CHECK();
     k_fb_decide<<<1, 1024, 0, st>>>(part, P, fb->tol, outer, summary_dev, fb_summary_dev, mask, order, n_order, batch);
     GSB_LAUNCH_CHECK();
     GSB_CUDA(cudaMemcpyAsync(ctx->h_counter, n_order, sizeof(int), cudaMemcpyDeviceToHost, st));
     GSB_CUDA(cudaStreamSynchronize(st));
+    if (ctx->timing) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, ev[0], ev[1]) == cudaSuccess) ctx->timing_acc[0] += ms, ctx->timing_acc[1] += 1.0;
+      if (with_wall && cudaEventElapsedTime(&ms, ev[2], ev[3]) == cudaSuccess) ctx->timing_acc[2] += ms, ctx->timing_acc[3] += 1.0;
+    }
     if (ctx->h_counter[0] == 0) {
       ++outer;
       break;
     }
   }
+  for (auto &e : ev)
+    if (e) cudaEventDestroy(e);
   cleanup();
   return rc;
+}
+
+int gsb_timing(gsb_ctx *ctx, int enable, double *out4, int reset) {
+  GSB_REQUIRE(ctx, "gsb_timing: NULL context");
+  ctx->timing = enable != 0;
+  if (out4)
+    for (int i = 0; i < 4; ++i) out4[i] = ctx->timing_acc[i];
+  if (reset)
+    for (double &v : ctx->timing_acc) v = 0.0;
+  return GSB_OK;
 }
 
 }  // extern "C"

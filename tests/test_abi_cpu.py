@@ -194,6 +194,7 @@ def test_ctypes_struct_layouts_match_the_c_header(tmp_path):
     if shutil.which("gcc") is None:
         pytest.skip("no C compiler")
     mirrors = {"gsb_profile": _lib.gsb_profile, "gsb_picard_params": _lib.gsb_picard_params,
+               "gsb_free_boundary_params": _lib.gsb_free_boundary_params,
                "gsb_slab_level_desc": slab._LevelDesc, "gsb_slab_halo_desc": slab._HaloDesc}
     lines = []
     for cname, cls in mirrors.items():
