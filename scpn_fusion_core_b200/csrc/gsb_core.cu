@@ -293,6 +293,11 @@ void gsb_destroy(gsb_ctx *ctx) {
   if (ctx->mg_bc) cudaFree(ctx->mg_bc);
   if (ctx->split_src) cudaFree(ctx->split_src);
   if (ctx->x_alt) cudaFree(ctx->x_alt);
+  if (ctx->gemm_ws) cudaFree(ctx->gemm_ws);
+  if (ctx->fb_old) cudaFree(ctx->fb_old);
+  if (ctx->fb_part) cudaFree(ctx->fb_part);
+  if (ctx->fb_wall) cudaFree(ctx->fb_wall);
+  if (ctx->fb_ints) cudaFree(ctx->fb_ints);
   if (ctx->h_counter) cudaFreeHost(ctx->h_counter);
   delete ctx;
 }

@@ -176,188 +176,167 @@ k_wall_matrix(const double *__restrict__ rrow, const double *__restrict__ zax, i
 
 // ------------------------------------------------------------------------------------------
 // a18  wall[b][w] = sum_s M[w][s] * (J[b][interior s] * dA)
-// C[B x Nw] = X[B x K] * M^T[K x Nw] on the FP64 tensor pipe (mma.sync m8n8k4 f64 = DMMA).
-// CTA tile 64(b) x 64(w), K step 16, 256 threads = 8 warps laid out 2(b) x 4(w); each warp owns a
-// 32 x 16 sub-tile = 4 x 2 m8n8 accumulators.  The interior gather and the *dA scaling are fused
-// into the X tile load.  Split-K over gridDim.z with a deterministic second-pass reduction.
+// C[B x Nw] = X[B x K] * M^T[K x Nw] on the FP64 tensor pipe: mma.sync m8n8k4 f64 (SASS DMMA.8x8x4, the only
+// native FP64 MMA shape on sm_100a - the m16n8k{4,8,16} forms compile to sequences of it; tcgen05 has no
+// FP64 kind).  The pipe retires one DMMA (512 flop) per ~4 cycles per SM, i.e. 128 flop/clk/SM - the same
+// rate as 64 DFMA lanes - so the kernel is about keeping that one pipe fed without bubbles:
+//   * persistent stream-K: the (output tile, K tile) space is linearised and cut into gridDim.x equal runs,
+//     one CTA per SM, so every SM issues DMMAs from the first to the last cycle (no wave quantisation:
+//     256 output tiles of 128x64 over 296 CTA slots cost the previous kernel 14 %).  A tile that is cut
+//     writes partial sums; k_wall_reduce adds them in a fixed order (deterministic, no atomics);
+//   * CTA tile 128(b) x 128(w) x 16(k), 16 warps of 32x32 (4x4 accumulator fragments: 8 LDS.64 feed 16 DMMA);
+//   * operands keep their global K-contiguous layout in shared memory, rows padded to 20 doubles: fragment
+//     loads (row = lane/4, k = lane%4) and the 8-byte cp.async fills (16 consecutive k per row) are both
+//     bank-conflict free;
+//   * 4-stage cp.async pipeline (zero-fill for the ragged last chunk of every grid row and for rows beyond
+//     the batch / the wall), one barrier per K tile;
+//   * the interior gather is fused into the X-tile addressing: K is walked as (interior row, 16-column
+//     chunk), so a K tile never straddles a grid row and needs no per-element index arithmetic; dA is
+//     applied to the accumulators.
 // ------------------------------------------------------------------------------------------
-constexpr int GB = 64, GW = 64, GK = 16;
+constexpr int SB = 128, SW = 128, SK = 16, SLD = 20, SNST = 4, STHREADS = 512;
+constexpr int kSkStageDoubles = (SB + SW) * SLD;
+constexpr int kSkSmem = SNST * kSkStageDoubles * (int)sizeof(double);
 
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                : "+d"(c0), "+d"(c1)
                : "d"(a), "d"(b));
 }
+__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int sz = valid ? 8 : 0;  // src-size 0: the 8 destination bytes are zero-filled
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-__global__ void __launch_bounds__(256)
-k_wall_gemm(const double *__restrict__ M, const double *__restrict__ J, int nz, int nr, int batch,
-            int nwall, int nint, double dA, int k_per_split, double *__restrict__ out /*[split][B][Nw]*/) {
-  __shared__ double sX[GK][GB + 4];  // [k][b]
-  __shared__ double sM[GK][GW + 4];  // [k][w]
-  const int b0 = blockIdx.x * GB, w0 = blockIdx.y * GW;
-  const int kbeg = blockIdx.z * k_per_split;
-  const int kend = min(nint, kbeg + k_per_split);
+struct WallGemmArgs {
+  const double *M, *J;
+  double *out;    // [B][Nw]
+  double *part;   // [tile][max_parts][SB*SW] partial sums of tiles cut by the stream-K schedule
+  int nz, nr, batch, nwall, nint;
+  int ntk;        // K tiles per output tile
+  int nwt;        // output tiles along w
+  long long total, spc;  // linearised (tile, K tile) steps; steps per CTA
+  int max_parts;
+  double dA;
+};
+
+__global__ void __launch_bounds__(STHREADS, 1) k_wall_gemm_sk(const WallGemmArgs a) {
+  extern __shared__ double gsm[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int wb = (warp >> 2) * 32, ww = (warp & 3) * 16;
+  const int wb = (warp >> 2) * 32, ww = (warp & 3) * 32;
   const int gid = lane >> 2, tig = lane & 3;
-  const size_t n = (size_t)nz * nr;
-  double acc[4][2][2];
+  const int lk = tid & 15, lr = tid >> 4;  // loader role: column lk of rows lr, lr+32, lr+64, lr+96
+  const int ncol = a.nr - 2, cpr = (ncol + SK - 1) / SK;
+  const size_t n = (size_t)a.nz * a.nr;
+  const long long s_begin = (long long)blockIdx.x * a.spc, s_end = min(a.total, s_begin + a.spc);
+  long long s = s_begin;
+  while (s < s_end) {
+    const int tile = (int)(s / a.ntk), k_lo = (int)(s - (long long)tile * a.ntk);
+    const int k_hi = (int)min((long long)a.ntk, k_lo + (s_end - s));
+    const int nk = k_hi - k_lo;
+    const int b0 = (tile / a.nwt) * SB, w0 = (tile % a.nwt) * SW;
+    double acc[4][4][2];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-
-  for (int k0 = kbeg; k0 < kend; k0 += GK) {
-    // X tile: 64 b x 16 k ; thread -> (b = tid/4 , 4 consecutive k)
-    {
-      const int bb = tid >> 2, kk = (tid & 3) * 4;
+      for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    const double *jbase[4], *mbase[4];
+    bool jok[4], mok[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int b = b0 + lr + 32 * q, w = w0 + lr + 32 * q;
+      jok[q] = b < a.batch;
+      mok[q] = w < a.nwall;
+      jbase[q] = a.J + (size_t)min(b, a.batch - 1) * n + a.nr + 1 + lk;
+      mbase[q] = a.M + (size_t)min(w, a.nwall - 1) * a.nint + lk;
+    }
+    int t_row = k_lo / cpr, t_chunk = k_lo - t_row * cpr;  // position of the NEXT K tile to be issued
+    auto issue = [&](int stage) {
+      const int c0 = t_chunk * SK;
+      const bool kok = c0 + lk < ncol;
+      double *sX = gsm + stage * kSkStageDoubles, *sM = sX + SB * SLD;
+      const size_t joff = (size_t)t_row * a.nr + c0, moff = (size_t)t_row * ncol + c0;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const int s = k0 + kk + q;
-        double v = 0.0;
-        if (s < kend && b0 + bb < batch) {
-          const int iz = 1 + s / (nr - 2), ir = 1 + s % (nr - 2);
-          v = J[(size_t)(b0 + bb) * n + (size_t)iz * nr + ir] * dA;
+        cp_async8(sX + (lr + 32 * q) * SLD + lk, jbase[q] + (kok ? joff : 0), kok && jok[q]);
+        cp_async8(sM + (lr + 32 * q) * SLD + lk, mbase[q] + (kok ? moff : 0), kok && mok[q]);
+      }
+      if (++t_chunk == cpr) t_chunk = 0, ++t_row;
+    };
+#pragma unroll
+    for (int st = 0; st < SNST - 1; ++st) {
+      if (st < nk) issue(st);
+      cp_async_commit();
+    }
+    for (int i = 0; i < nk; ++i) {
+      cp_async_wait<SNST - 2>();
+      __syncthreads();  // tile i has landed for everybody; everybody is done reading the stage refilled next
+      if (i + SNST - 1 < nk) issue((i + SNST - 1) % SNST);
+      cp_async_commit();
+      const double *sX = gsm + (i % SNST) * kSkStageDoubles, *sM = sX + SB * SLD;
+#pragma unroll
+      for (int ks = 0; ks < SK; ks += 4) {
+        double af[4], bf[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) af[u] = sX[(wb + u * 8 + gid) * SLD + ks + tig];  // A[row = gid][k = tig]
+#pragma unroll
+        for (int u = 0; u < 4; ++u) bf[u] = sM[(ww + u * 8 + gid) * SLD + ks + tig];  // B[k = tig][col = gid]
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int v = 0; v < 4; ++v) dmma884(acc[u][v][0], acc[u][v][1], af[u], bf[v]);
+      }
+    }
+    cp_async_wait<0>();
+    __syncthreads();  // the stages are refilled by the next segment
+    // C fragment: row = gid, cols = 2*tig, 2*tig + 1
+    const bool whole = (k_lo == 0 && k_hi == a.ntk);
+    if (whole) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const int b = b0 + wb + u * 8 + gid, w = w0 + ww + v * 8 + 2 * tig;
+          if (b < a.batch) {
+            if (w < a.nwall) a.out[(size_t)b * a.nwall + w] = acc[u][v][0] * a.dA;
+            if (w + 1 < a.nwall) a.out[(size_t)b * a.nwall + w + 1] = acc[u][v][1] * a.dA;
+          }
         }
-        sX[kk + q][bb] = v;
-      }
+    } else {
+      const int c_first = (int)(((long long)tile * a.ntk) / a.spc);
+      double *pp = a.part + ((size_t)tile * a.max_parts + (blockIdx.x - c_first)) * (SB * SW);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const int lb = wb + u * 8 + gid, lw = ww + v * 8 + 2 * tig;
+          *reinterpret_cast<double2 *>(pp + lb * SW + lw) = make_double2(acc[u][v][0], acc[u][v][1]);
+        }
     }
-    // M tile: 64 w x 16 k ; M is [w][s] row-major so k is contiguous
-    {
-      const int wwl = tid >> 2, kk = (tid & 3) * 4;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int s = k0 + kk + q;
-        double v = 0.0;
-        if (s < kend && w0 + wwl < nwall) v = M[(size_t)(w0 + wwl) * nint + s];
-        sM[kk + q][wwl] = v;
-      }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int ks = 0; ks < GK; ks += 4) {
-      double a[4], bfr[2];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = sX[ks + tig][wb + i * 8 + gid];    // A[row=gid][k=tig]
-#pragma unroll
-      for (int j = 0; j < 2; ++j) bfr[j] = sM[ks + tig][ww + j * 8 + gid];  // B[k=tig][col=gid]
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 2; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], bfr[j]);
-    }
-    __syncthreads();
+    s += nk;
   }
-  // C fragment: row = gid, cols = 2*tig, 2*tig+1
-  double *o = out + (size_t)blockIdx.z * batch * nwall;
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const int b = b0 + wb + i * 8 + gid;
-      const int w = w0 + ww + j * 8 + 2 * tig;
-      if (b < batch) {
-        if (w < nwall) o[(size_t)b * nwall + w] = acc[i][j][0];
-        if (w + 1 < nwall) o[(size_t)b * nwall + w + 1] = acc[i][j][1];
-      }
-    }
 }
 
-// Large-batch variant: CTA tile 128(b) x 64(w), K step 16, 8 warps laid out 4(b) x 2(w), each warp a
-// 32 x 32 sub-tile = 4 x 4 m8n8k4 accumulators (two shared loads per DMMA instead of three quarters
-// of one per DMMA... 8 LDS.64 feed 16 DMMA).  The K axis is walked as (interior row, 16-column
-// chunk) so a K tile never straddles a grid row: no integer division in the gather, and the
-// 16-column chunks of a row are contiguous in J and in M.  The next tile is fetched into registers
-// while the current one is multiplied (one barrier pair per K step, global latency hidden).
-constexpr int HB = 128, HW = 64, HK = 16;
-__global__ void __launch_bounds__(256, 2)
-k_wall_gemm_big(const double *__restrict__ M, const double *__restrict__ J, int nz, int nr, int batch, int nwall,
-                int nint, double dA, int tiles_per_split, double *__restrict__ out /*[split][B][Nw]*/) {
-  extern __shared__ double gsm[];  // two stages of { sX[HK][HB+4] ([k][b]), sM[HK][HW+4] ([k][w]) }
-  constexpr int LDX = HB + 4, LDM = HW + 4, STAGE = HK * (LDX + LDM);
-  const int b0 = blockIdx.x * HB, w0 = blockIdx.y * HW;
-  const int ncol = nr - 2;                      // interior columns per grid row
-  const int cpr = (ncol + HK - 1) / HK;         // 16-column chunks per row
-  const int ntiles = (nz - 2) * cpr;
-  const int t_beg = blockIdx.z * tiles_per_split, t_end = min(ntiles, t_beg + tiles_per_split);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int wb = (warp >> 1) * 32, ww = (warp & 1) * 32;
-  const int gid = lane >> 2, tig = lane & 3;
-  const size_t n = (size_t)nz * nr;
-  // loader roles: X tile 128 b x 16 k -> thread (b = tid/2, 8 consecutive k); M tile 64 w x 16 k -> (w = tid/4, 4 k)
-  const int xb = tid >> 1, xk = (tid & 1) * 8;
-  const int mw = tid >> 2, mk = (tid & 3) * 4;
-  const bool xb_ok = b0 + xb < batch, mw_ok = w0 + mw < nwall;
-  const double *jrow = J + (size_t)min(b0 + xb, batch - 1) * n;
-  const double *mrow = M + (size_t)min(w0 + mw, nwall - 1) * nint;
-  double acc[4][4][2];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-  double px[8], pm[4];
-  auto fetch = [&](int t) {
-    const int row = t / cpr, c0 = (t - row * cpr) * HK;  // once per K tile, not per element
-    const double *jp = jrow + (size_t)(row + 1) * nr + 1 + c0 + xk;
-    const double *mp = mrow + (size_t)row * ncol + c0 + mk;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) px[q] = (xb_ok && c0 + xk + q < ncol) ? jp[q] * dA : 0.0;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) pm[q] = (mw_ok && c0 + mk + q < ncol) ? mp[q] : 0.0;
-  };
-  auto stash = [&](int stage) {
-    double *sX = gsm + stage * STAGE, *sM = sX + HK * LDX;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) sX[(xk + q) * LDX + xb] = px[q];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) sM[(mk + q) * LDM + mw] = pm[q];
-  };
-  if (t_beg < t_end) {
-    fetch(t_beg);
-    stash(0);
+// fixed-order sum of the partial tiles (tiles solved by a single CTA were written directly)
+__global__ void __launch_bounds__(256) k_wall_reduce(const WallGemmArgs a) {
+  const int tile = blockIdx.y;
+  const int c_first = (int)(((long long)tile * a.ntk) / a.spc);
+  const int c_last = (int)(((long long)(tile + 1) * a.ntk - 1) / a.spc);
+  const int np = c_last - c_first + 1;
+  if (np == 1) return;
+  const int b0 = (tile / a.nwt) * SB, w0 = (tile % a.nwt) * SW;
+  const double *pp = a.part + (size_t)tile * a.max_parts * (SB * SW);
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < SB * SW; e += gridDim.x * blockDim.x) {
+    const int b = b0 + e / SW, w = w0 + e % SW;
+    if (b >= a.batch || w >= a.nwall) continue;
+    double sum = pp[e];
+    for (int p = 1; p < np; ++p) sum += pp[(size_t)p * (SB * SW) + e];
+    a.out[(size_t)b * a.nwall + w] = sum * a.dA;
   }
-  __syncthreads();
-  int cur = 0;
-  for (int t = t_beg; t < t_end; ++t) {
-    if (t + 1 < t_end) fetch(t + 1);  // global loads of the next tile fly during the multiply
-    const double *sX = gsm + cur * STAGE, *sM = sX + HK * LDX;
-#pragma unroll
-    for (int ks = 0; ks < HK; ks += 4) {
-      double a[4], bfr[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = sX[(ks + tig) * LDX + wb + i * 8 + gid];    // A[row=gid][k=tig]
-#pragma unroll
-      for (int j = 0; j < 4; ++j) bfr[j] = sM[(ks + tig) * LDM + ww + j * 8 + gid];  // B[k=tig][col=gid]
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], bfr[j]);
-    }
-    if (t + 1 < t_end) stash(1 - cur);  // the other stage was last read before the previous barrier
-    __syncthreads();
-    cur ^= 1;
-  }
-  double *o = out + (size_t)blockIdx.z * batch * nwall;
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int b = b0 + wb + i * 8 + gid;
-      const int w = w0 + ww + j * 8 + 2 * tig;
-      if (b < batch) {
-        if (w < nwall) o[(size_t)b * nwall + w] = acc[i][j][0];
-        if (w + 1 < nwall) o[(size_t)b * nwall + w + 1] = acc[i][j][1];
-      }
-    }
-}
-
-__global__ void k_splitk_reduce(const double *__restrict__ part, int splits, size_t total,
-                                double *__restrict__ out) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  double a = 0.0;
-  for (int s = 0; s < splits; ++s) a += part[(size_t)s * total + i];
-  out[i] = a;
 }
 
 __global__ void k_wall_scatter(const double *__restrict__ wall, double *__restrict__ bc, int nz, int nr,
@@ -459,47 +438,38 @@ int gsb_wall_flux(gsb_ctx *ctx, const double *m_dev, const double *jphi_dev, dou
                   int batch, void *stream) {
   GSB_REQUIRE(ctx && m_dev && jphi_dev && wall_dev, "gsb_wall_flux: NULL argument");
   GSB_REQUIRE(batch >= 1, "gsb_wall_flux: bad batch");
+  GSB_REQUIRE(ctx->nz >= 3 && ctx->nr >= 3, "gsb_wall_flux: grid has no interior");
   GSB_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = (cudaStream_t)stream;
-  const int nw = ctx->n_wall, ni = ctx->n_int;
-  if (batch >= HB) {  // large batches: 128 x 64 tiles, register double buffering
-    const int cpr = (ctx->nr - 2 + HK - 1) / HK, ntiles = (ctx->nz - 2) * cpr;
-    const int ctas = ((batch + HB - 1) / HB) * ((nw + HW - 1) / HW);
-    int splits = 1;
-    while (ctas * splits < 2 * ctx->num_sms && splits < 16 && ntiles / (splits * 2) >= 64) splits *= 2;
-    const int tps = (ntiles + splits - 1) / splits;
-    splits = (ntiles + tps - 1) / tps;
-    double *part = wall_dev;
-    if (splits > 1) GSB_CUDA(cudaMallocAsync(&part, (size_t)splits * batch * nw * sizeof(double), st));
-    constexpr int kBigSmem = 2 * HK * (HB + 4 + HW + 4) * (int)sizeof(double);
-    GSB_SMEM_OPT_IN(k_wall_gemm_big, kBigSmem);
-    k_wall_gemm_big<<<dim3((batch + HB - 1) / HB, (nw + HW - 1) / HW, splits), 256, kBigSmem, st>>>(
-        m_dev, jphi_dev, ctx->nz, ctx->nr, batch, nw, ni, dA, tps, part);
-    GSB_LAUNCH_CHECK();
-    if (splits > 1) {
-      const size_t total = (size_t)batch * nw;
-      k_splitk_reduce<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(part, splits, total, wall_dev);
-      GSB_LAUNCH_CHECK();
-      GSB_CUDA(cudaFreeAsync(part, st));
-    }
-    return GSB_OK;
+  WallGemmArgs a{};
+  a.M = m_dev;
+  a.J = jphi_dev;
+  a.out = wall_dev;
+  a.nz = ctx->nz, a.nr = ctx->nr, a.batch = batch, a.nwall = ctx->n_wall, a.nint = ctx->n_int;
+  a.dA = dA;
+  const int cpr = (ctx->nr - 2 + SK - 1) / SK;
+  a.ntk = (ctx->nz - 2) * cpr;
+  a.nwt = (a.nwall + SW - 1) / SW;
+  const int n_tiles = ((batch + SB - 1) / SB) * a.nwt;
+  a.total = (long long)n_tiles * a.ntk;
+  const int grid = (int)std::min<long long>(ctx->num_sms, a.total);
+  a.spc = (a.total + grid - 1) / grid;
+  a.max_parts = (int)((a.ntk + a.spc - 1) / a.spc) + 1;
+  const size_t need = (size_t)n_tiles * a.max_parts * SB * SW * sizeof(double);
+  if (ctx->gemm_ws_bytes < need) {  // grow-only workspace: no allocation in steady state
+    if (ctx->gemm_ws) GSB_CUDA(cudaFree(ctx->gemm_ws));
+    ctx->gemm_ws = nullptr;
+    ctx->gemm_ws_bytes = 0;
+    GSB_CUDA(cudaMalloc(&ctx->gemm_ws, need));
+    ctx->gemm_ws_bytes = need;
   }
-  const int tiles = ((batch + GB - 1) / GB) * ((nw + GW - 1) / GW);
-  int splits = 1;
-  while (tiles * splits < 148 * 2 && splits < 32 && ni / (splits * 2) >= 512) splits *= 2;
-  int kps = (ni + splits - 1) / splits;
-  kps = ((kps + GK - 1) / GK) * GK;
-  splits = (ni + kps - 1) / kps;
-  double *part = wall_dev;
-  if (splits > 1) GSB_CUDA(cudaMallocAsync(&part, (size_t)splits * batch * nw * sizeof(double), st));
-  k_wall_gemm<<<dim3((batch + GB - 1) / GB, (nw + GW - 1) / GW, splits), 256, 0, st>>>(
-      m_dev, jphi_dev, ctx->nz, ctx->nr, batch, nw, ni, dA, kps, part);
+  a.part = ctx->gemm_ws;
+  GSB_SMEM_OPT_IN(k_wall_gemm_sk, kSkSmem);
+  k_wall_gemm_sk<<<grid, STHREADS, kSkSmem, st>>>(a);
   GSB_LAUNCH_CHECK();
-  if (splits > 1) {
-    const size_t total = (size_t)batch * nw;
-    k_splitk_reduce<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(part, splits, total, wall_dev);
+  if (a.spc % a.ntk != 0) {  // the runs do not end on tile boundaries: some tiles are cut
+    k_wall_reduce<<<dim3(16, n_tiles), 256, 0, st>>>(a);
     GSB_LAUNCH_CHECK();
-    GSB_CUDA(cudaFreeAsync(part, st));
   }
   return GSB_OK;
 }

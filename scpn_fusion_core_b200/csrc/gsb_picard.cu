@@ -1966,22 +1966,16 @@ int gsb_free_boundary_solve(gsb_ctx *ctx, const gsb_picard_params *p, const gsb_
   const size_t n = ctx->n;
   const int nz = ctx->nz, nr = ctx->nr, nw = ctx->n_wall;
   // workspace: previous iterate, masks / work list, reduction partials, plasma wall flux
-  double *old = nullptr, *part = nullptr, *wall = nullptr;
-  int *ints = nullptr;
-  GSB_CUDA(cudaMallocAsync(&old, (size_t)batch * n * sizeof(double), st));
-  GSB_CUDA(cudaMallocAsync(&part, (size_t)batch * kPT * 2 * sizeof(double), st));
-  GSB_CUDA(cudaMallocAsync(&ints, ((size_t)2 * batch + 2) * sizeof(int), st));
-  if (wall_m_dev) GSB_CUDA(cudaMallocAsync(&wall, (size_t)batch * nw * sizeof(double), st));
-  int *mask = ints, *order = ints + batch, *n_order = ints + 2 * batch;
+  const size_t cap = (size_t)ctx->batch_cap;
+  if (!ctx->fb_old) GSB_CUDA(cudaMalloc(&ctx->fb_old, cap * n * sizeof(double)));
+  if (!ctx->fb_part) GSB_CUDA(cudaMalloc(&ctx->fb_part, cap * kPT * 2 * sizeof(double)));
+  if (!ctx->fb_ints) GSB_CUDA(cudaMalloc(&ctx->fb_ints, (2 * cap + 2) * sizeof(int)));
+  if (wall_m_dev && !ctx->fb_wall) GSB_CUDA(cudaMalloc(&ctx->fb_wall, cap * nw * sizeof(double)));
+  double *old = ctx->fb_old, *part = ctx->fb_part, *wall = wall_m_dev ? ctx->fb_wall : nullptr;
+  int *mask = ctx->fb_ints, *order = ctx->fb_ints + batch, *n_order = ctx->fb_ints + 2 * batch;
   const int P = partials_for(nz, nr);
   const int blocks = (int)std::min<size_t>((n + 255) / 256, 64);
   int rc = GSB_OK;
-  auto cleanup = [&]() {
-    cudaFreeAsync(old, st);
-    cudaFreeAsync(part, st);
-    cudaFreeAsync(ints, st);
-    if (wall) cudaFreeAsync(wall, st);
-  };
   k_fb_init<<<(batch + 255) / 256, 256, 0, st>>>(mask, order, n_order, fb_summary_dev, batch);
   GSB_LAUNCH_CHECK();
   const double dA = ctx->dr * ctx->dz;
@@ -2022,7 +2016,6 @@ int gsb_free_boundary_solve(gsb_ctx *ctx, const gsb_picard_params *p, const gsb_
   }
   for (auto &e : ev)
     if (e) cudaEventDestroy(e);
-  cleanup();
   return rc;
 }
 

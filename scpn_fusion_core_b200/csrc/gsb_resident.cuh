@@ -82,6 +82,10 @@ __device__ __forceinline__ int split_index(int nz, int hw, int iz, int ir) {
 // ddiv_y (and to IEEE a/b) whenever the quotient is finite; a non-finite quotient comes out as NaN
 // instead of +-inf, which every caller treats the same way (non-finite => diverged).
 __device__ __forceinline__ double ddiv_yf(double a, double b, double y) {
+#ifdef GSB_FMA
+  (void)b;
+  return a * y;
+#endif
   const double q = __dmul_rn(a, y);
   const double r = __fma_rn(-b, q, a);
   return __fma_rn(r, y, q);
