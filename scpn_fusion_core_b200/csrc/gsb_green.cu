@@ -6,6 +6,8 @@
 //  * lane-C plasma -> wall response matrix and its batched contraction on the FP64 tensor pipe
 #include "gsb_internal.cuh"
 
+#include <cstdlib>
+
 namespace gsb {
 
 __constant__ double c_ellpk_P[11] = {
@@ -194,9 +196,18 @@ k_wall_matrix(const double *__restrict__ rrow, const double *__restrict__ zax, i
 //     chunk), so a K tile never straddles a grid row and needs no per-element index arithmetic; dA is
 //     applied to the accumulators.
 // ------------------------------------------------------------------------------------------
-constexpr int SB = 128, SW = 128, SK = 16, SLD = 20, SNST = 4, STHREADS = 512;
-constexpr int kSkStageDoubles = (SB + SW) * SLD;
-constexpr int kSkSmem = SNST * kSkStageDoubles * (int)sizeof(double);
+// Tile configuration: BM(b) x BN(w) x BK, NST cp.async stages, (BM/32) x (BN/32) warps of 32x32, CPS CTAs per SM.
+template <int BM_, int BN_, int BK_, int NST_, int CPS_, bool MBAR_ = false>
+struct GemmCfg {
+  static constexpr int BM = BM_, BN = BN_, BK = BK_, NST = NST_, CPS = CPS_;
+  static constexpr bool MBAR = MBAR_;  // mbarrier full/empty pipeline instead of one __syncthreads per K tile
+  static constexpr int LD = BK + 4;  // row pitch in doubles: (4*row + k) mod 16 distinct over a half warp -> no bank conflicts
+  static constexpr int THREADS = (BM / 32) * (BN / 32) * 32;
+  static constexpr int WN = BN / 32;  // warps along w
+  static constexpr int STAGE = (BM + BN) * LD;
+  static constexpr int SMEM = NST * STAGE * (int)sizeof(double) + (MBAR_ ? 2 * NST * 8 : 0);
+  static constexpr int RP = THREADS / BK;  // rows filled per loader pass
+};
 
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -211,11 +222,34 @@ __device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc, 
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// mbarrier helpers (shared::cta, 32-bit shared addresses)
+__device__ __forceinline__ void mbar_init(unsigned bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// arrive on `bar` when all cp.async issued so far by this thread have landed (counts as one of the expected arrivals)
+__device__ __forceinline__ void mbar_arrive_on_cp_async(unsigned bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar), "r"(parity)
+      : "memory");
+}
 
 struct WallGemmArgs {
   const double *M, *J;
   double *out;    // [B][Nw]
-  double *part;   // [tile][max_parts][SB*SW] partial sums of tiles cut by the stream-K schedule
+  double *part;   // [tile][max_parts][BM*BN] partial sums of tiles cut by the stream-K schedule
   int nz, nr, batch, nwall, nint;
   int ntk;        // K tiles per output tile
   int nwt;        // output tiles along w
@@ -224,75 +258,125 @@ struct WallGemmArgs {
   double dA;
 };
 
-__global__ void __launch_bounds__(STHREADS, 1) k_wall_gemm_sk(const WallGemmArgs a) {
+template <class C>
+__global__ void __launch_bounds__(C::THREADS, C::CPS) k_wall_gemm_sk(const WallGemmArgs a) {
   extern __shared__ double gsm[];
+  constexpr int BM = C::BM, BN = C::BN, BK = C::BK, LD = C::LD, NST = C::NST, RP = C::RP;
+  constexpr int XQ = BM / RP, MQ = BN / RP;  // loader passes per tile
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int wb = (warp >> 2) * 32, ww = (warp & 3) * 32;
+  const int wb = (warp / C::WN) * 32, ww = (warp % C::WN) * 32;
   const int gid = lane >> 2, tig = lane & 3;
-  const int lk = tid & 15, lr = tid >> 4;  // loader role: column lk of rows lr, lr+32, lr+64, lr+96
-  const int ncol = a.nr - 2, cpr = (ncol + SK - 1) / SK;
+  const int lk = tid % BK, lr = tid / BK;  // loader role: column lk of rows lr, lr+RP, ...
+  const int ncol = a.nr - 2, cpr = (ncol + BK - 1) / BK;
   const size_t n = (size_t)a.nz * a.nr;
   const long long s_begin = (long long)blockIdx.x * a.spc, s_end = min(a.total, s_begin + a.spc);
   long long s = s_begin;
+  // mbarrier pipeline: full[st] completes when all THREADS loaders' copies of a K tile have landed in stage st,
+  // empty[st] when all warps have finished reading it.  A warp refills a stage only one whole K tile after it
+  // read it, so warps may drift apart by up to a tile instead of meeting at a CTA barrier every K tile.
+  const unsigned bar_full = (unsigned)__cvta_generic_to_shared(gsm + NST * C::STAGE), bar_empty = bar_full + NST * 8;
+  unsigned it = 0;  // K tiles consumed by this CTA so far (stage = it % NST, phase parity = (it / NST) & 1)
+  if (C::MBAR) {
+    if (tid == 0)
+      for (int st = 0; st < NST; ++st) mbar_init(bar_full + 8 * st, C::THREADS), mbar_init(bar_empty + 8 * st, C::THREADS / 32);
+    __syncthreads();
+  }
   while (s < s_end) {
     const int tile = (int)(s / a.ntk), k_lo = (int)(s - (long long)tile * a.ntk);
     const int k_hi = (int)min((long long)a.ntk, k_lo + (s_end - s));
     const int nk = k_hi - k_lo;
-    const int b0 = (tile / a.nwt) * SB, w0 = (tile % a.nwt) * SW;
+    const int b0 = (tile / a.nwt) * BM, w0 = (tile % a.nwt) * BN;
     double acc[4][4][2];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-    const double *jbase[4], *mbase[4];
-    bool jok[4], mok[4];
+    // Loader, kept lean on purpose: every non-DMMA instruction in this loop costs tensor-pipe time (measured:
+    // 40 integer instructions per K tile = 7 %, tools/ubench/dmma_pipe.cu).  Per thread and segment: XQ + MQ
+    // byte pointers fixed for the whole segment; per K tile one CTA-uniform byte offset per operand.  Rows
+    // beyond the batch / the wall are clamped to the last valid row (their results are never stored), so only
+    // the ragged last 16-column chunk of a grid row needs a zero fill, and only on the M side: the X element
+    // it meets is the (finite) wall column of J.
+    const char *jq[XQ], *mq[MQ];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int b = b0 + lr + 32 * q, w = w0 + lr + 32 * q;
-      jok[q] = b < a.batch;
-      mok[q] = w < a.nwall;
-      jbase[q] = a.J + (size_t)min(b, a.batch - 1) * n + a.nr + 1 + lk;
-      mbase[q] = a.M + (size_t)min(w, a.nwall - 1) * a.nint + lk;
-    }
+    for (int q = 0; q < XQ; ++q)
+      jq[q] = reinterpret_cast<const char *>(a.J + (size_t)min(b0 + lr + RP * q, a.batch - 1) * n + a.nr + 1 + lk);
+#pragma unroll
+    for (int q = 0; q < MQ; ++q)
+      mq[q] = reinterpret_cast<const char *>(a.M + (size_t)min(w0 + lr + RP * q, a.nwall - 1) * a.nint + lk);
+    const unsigned s_thread = (unsigned)__cvta_generic_to_shared(gsm + lr * LD + lk);
     int t_row = k_lo / cpr, t_chunk = k_lo - t_row * cpr;  // position of the NEXT K tile to be issued
     auto issue = [&](int stage) {
-      const int c0 = t_chunk * SK;
+      const int c0 = t_chunk * BK;
       const bool kok = c0 + lk < ncol;
-      double *sX = gsm + stage * kSkStageDoubles, *sM = sX + SB * SLD;
-      const size_t joff = (size_t)t_row * a.nr + c0, moff = (size_t)t_row * ncol + c0;
+      const size_t to_j = ((size_t)t_row * a.nr + c0) * sizeof(double);
+      const size_t to_m = kok ? ((size_t)t_row * ncol + c0) * sizeof(double) : 0;
+      const int msz = kok ? 8 : 0;  // src-size 0: the 8 destination bytes are zero-filled
+      const unsigned sx = s_thread + stage * (C::STAGE * (int)sizeof(double));
+      const unsigned smm = sx + BM * LD * (int)sizeof(double);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        cp_async8(sX + (lr + 32 * q) * SLD + lk, jbase[q] + (kok ? joff : 0), kok && jok[q]);
-        cp_async8(sM + (lr + 32 * q) * SLD + lk, mbase[q] + (kok ? moff : 0), kok && mok[q]);
-      }
+      for (int q = 0; q < XQ; ++q)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sx + q * (RP * LD * 8)), "l"(jq[q] + to_j) : "memory");
+#pragma unroll
+      for (int q = 0; q < MQ; ++q)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smm + q * (RP * LD * 8)), "l"(mq[q] + to_m), "r"(msz)
+                     : "memory");
       if (++t_chunk == cpr) t_chunk = 0, ++t_row;
     };
+    auto produce = [&](unsigned j) {  // fill stage j % NST with the next K tile (tile number j of this CTA)
+      const unsigned sj = j % NST;
+      if (j >= (unsigned)NST) mbar_wait(bar_empty + 8 * sj, ((j / NST) & 1) ^ 1);  // its previous tile has been read by all
+      issue((int)sj);
+      mbar_arrive_on_cp_async(bar_full + 8 * sj);
+    };
+    if (C::MBAR) {
 #pragma unroll
-    for (int st = 0; st < SNST - 1; ++st) {
-      if (st < nk) issue(st);
-      cp_async_commit();
+      for (int st = 0; st < NST - 2; ++st)
+        if (st < nk) produce(it + st);
+    } else {
+#pragma unroll
+      for (int st = 0; st < NST - 1; ++st) {
+        if (st < nk) issue(st);
+        cp_async_commit();
+      }
     }
     for (int i = 0; i < nk; ++i) {
-      cp_async_wait<SNST - 2>();
-      __syncthreads();  // tile i has landed for everybody; everybody is done reading the stage refilled next
-      if (i + SNST - 1 < nk) issue((i + SNST - 1) % SNST);
-      cp_async_commit();
-      const double *sX = gsm + (i % SNST) * kSkStageDoubles, *sM = sX + SB * SLD;
+      int stage;
+      if (C::MBAR) {
+        stage = (int)((it + i) % NST);
+        if (i + NST - 2 < nk) produce(it + i + NST - 2);
+        mbar_wait(bar_full + 8 * stage, ((it + i) / NST) & 1);
+      } else {
+        stage = i % NST;
+        cp_async_wait<NST - 2>();
+        __syncthreads();  // tile i has landed for everybody; everybody is done reading the stage refilled next
+        if (i + NST - 1 < nk) issue((i + NST - 1) % NST);
+        cp_async_commit();
+      }
+      const double *sX = gsm + stage * C::STAGE, *sM = sX + BM * LD;
 #pragma unroll
-      for (int ks = 0; ks < SK; ks += 4) {
+      for (int ks = 0; ks < BK; ks += 4) {
         double af[4], bf[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) af[u] = sX[(wb + u * 8 + gid) * SLD + ks + tig];  // A[row = gid][k = tig]
+        for (int u = 0; u < 4; ++u) af[u] = sX[(wb + u * 8 + gid) * LD + ks + tig];  // A[row = gid][k = tig]
 #pragma unroll
-        for (int u = 0; u < 4; ++u) bf[u] = sM[(ww + u * 8 + gid) * SLD + ks + tig];  // B[k = tig][col = gid]
+        for (int u = 0; u < 4; ++u) bf[u] = sM[(ww + u * 8 + gid) * LD + ks + tig];  // B[k = tig][col = gid]
 #pragma unroll
         for (int u = 0; u < 4; ++u)
 #pragma unroll
           for (int v = 0; v < 4; ++v) dmma884(acc[u][v][0], acc[u][v][1], af[u], bf[v]);
       }
+      if (C::MBAR) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_empty + 8 * stage);
+      }
     }
-    cp_async_wait<0>();
-    __syncthreads();  // the stages are refilled by the next segment
+    if (C::MBAR) {
+      it += nk;
+    } else {
+      cp_async_wait<0>();
+      __syncthreads();  // the stages are refilled by the next segment
+    }
     // C fragment: row = gid, cols = 2*tig, 2*tig + 1
     const bool whole = (k_lo == 0 && k_hi == a.ntk);
     if (whole) {
@@ -308,13 +392,13 @@ __global__ void __launch_bounds__(STHREADS, 1) k_wall_gemm_sk(const WallGemmArgs
         }
     } else {
       const int c_first = (int)(((long long)tile * a.ntk) / a.spc);
-      double *pp = a.part + ((size_t)tile * a.max_parts + (blockIdx.x - c_first)) * (SB * SW);
+      double *pp = a.part + ((size_t)tile * a.max_parts + (blockIdx.x - c_first)) * (BM * BN);
 #pragma unroll
       for (int u = 0; u < 4; ++u)
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
           const int lb = wb + u * 8 + gid, lw = ww + v * 8 + 2 * tig;
-          *reinterpret_cast<double2 *>(pp + lb * SW + lw) = make_double2(acc[u][v][0], acc[u][v][1]);
+          *reinterpret_cast<double2 *>(pp + lb * BN + lw) = make_double2(acc[u][v][0], acc[u][v][1]);
         }
     }
     s += nk;
@@ -322,19 +406,19 @@ __global__ void __launch_bounds__(STHREADS, 1) k_wall_gemm_sk(const WallGemmArgs
 }
 
 // fixed-order sum of the partial tiles (tiles solved by a single CTA were written directly)
-__global__ void __launch_bounds__(256) k_wall_reduce(const WallGemmArgs a) {
+__global__ void __launch_bounds__(256) k_wall_reduce(const WallGemmArgs a, int BM, int BN) {
   const int tile = blockIdx.y;
   const int c_first = (int)(((long long)tile * a.ntk) / a.spc);
   const int c_last = (int)(((long long)(tile + 1) * a.ntk - 1) / a.spc);
   const int np = c_last - c_first + 1;
   if (np == 1) return;
-  const int b0 = (tile / a.nwt) * SB, w0 = (tile % a.nwt) * SW;
-  const double *pp = a.part + (size_t)tile * a.max_parts * (SB * SW);
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < SB * SW; e += gridDim.x * blockDim.x) {
-    const int b = b0 + e / SW, w = w0 + e % SW;
+  const int b0 = (tile / a.nwt) * BM, w0 = (tile % a.nwt) * BN;
+  const double *pp = a.part + (size_t)tile * a.max_parts * (BM * BN);
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < BM * BN; e += gridDim.x * blockDim.x) {
+    const int b = b0 + e / BN, w = w0 + e % BN;
     if (b >= a.batch || w >= a.nwall) continue;
     double sum = pp[e];
-    for (int p = 1; p < np; ++p) sum += pp[(size_t)p * (SB * SW) + e];
+    for (int p = 1; p < np; ++p) sum += pp[(size_t)p * (BM * BN) + e];
     a.out[(size_t)b * a.nwall + w] = sum * a.dA;
   }
 }
@@ -354,6 +438,35 @@ __global__ void k_wall_scatter(const double *__restrict__ wall, double *__restri
 }  // namespace gsb
 
 using namespace gsb;
+
+template <class C>
+static int wall_gemm_launch(gsb_ctx *ctx, WallGemmArgs a, cudaStream_t st) {
+  const int cpr = (ctx->nr - 2 + C::BK - 1) / C::BK;
+  a.ntk = (ctx->nz - 2) * cpr;
+  a.nwt = (a.nwall + C::BN - 1) / C::BN;
+  const int n_tiles = ((a.batch + C::BM - 1) / C::BM) * a.nwt;
+  a.total = (long long)n_tiles * a.ntk;
+  const int grid = (int)std::min<long long>((long long)ctx->num_sms * C::CPS, a.total);
+  a.spc = (a.total + grid - 1) / grid;
+  a.max_parts = (int)((a.ntk + a.spc - 1) / a.spc) + 1;
+  const size_t need = (size_t)n_tiles * a.max_parts * C::BM * C::BN * sizeof(double);
+  if (ctx->gemm_ws_bytes < need) {  // grow-only workspace: no allocation in steady state
+    if (ctx->gemm_ws) GSB_CUDA(cudaFree(ctx->gemm_ws));
+    ctx->gemm_ws = nullptr;
+    ctx->gemm_ws_bytes = 0;
+    GSB_CUDA(cudaMalloc(&ctx->gemm_ws, need));
+    ctx->gemm_ws_bytes = need;
+  }
+  a.part = ctx->gemm_ws;
+  GSB_SMEM_OPT_IN(k_wall_gemm_sk<C>, C::SMEM);
+  k_wall_gemm_sk<C><<<grid, C::THREADS, C::SMEM, st>>>(a);
+  GSB_LAUNCH_CHECK();
+  if (a.spc % a.ntk != 0) {  // the runs do not end on tile boundaries: some tiles are cut
+    k_wall_reduce<<<dim3(16, n_tiles), 256, 0, st>>>(a, C::BM, C::BN);
+    GSB_LAUNCH_CHECK();
+  }
+  return GSB_OK;
+}
 
 extern "C" {
 
@@ -447,31 +560,16 @@ int gsb_wall_flux(gsb_ctx *ctx, const double *m_dev, const double *jphi_dev, dou
   a.out = wall_dev;
   a.nz = ctx->nz, a.nr = ctx->nr, a.batch = batch, a.nwall = ctx->n_wall, a.nint = ctx->n_int;
   a.dA = dA;
-  const int cpr = (ctx->nr - 2 + SK - 1) / SK;
-  a.ntk = (ctx->nz - 2) * cpr;
-  a.nwt = (a.nwall + SW - 1) / SW;
-  const int n_tiles = ((batch + SB - 1) / SB) * a.nwt;
-  a.total = (long long)n_tiles * a.ntk;
-  const int grid = (int)std::min<long long>(ctx->num_sms, a.total);
-  a.spc = (a.total + grid - 1) / grid;
-  a.max_parts = (int)((a.ntk + a.spc - 1) / a.spc) + 1;
-  const size_t need = (size_t)n_tiles * a.max_parts * SB * SW * sizeof(double);
-  if (ctx->gemm_ws_bytes < need) {  // grow-only workspace: no allocation in steady state
-    if (ctx->gemm_ws) GSB_CUDA(cudaFree(ctx->gemm_ws));
-    ctx->gemm_ws = nullptr;
-    ctx->gemm_ws_bytes = 0;
-    GSB_CUDA(cudaMalloc(&ctx->gemm_ws, need));
-    ctx->gemm_ws_bytes = need;
+  // Tile configuration.  Default: 128x128x16 tiles, 4 stages, mbarrier full/empty pipeline, one CTA per SM.
+  // GSB_GEMM_VARIANT selects the measured alternatives (profiles/r2_wall_gemm.md): 1 = the same tiles with a
+  // __syncthreads() per K tile, 2 = 128x64 tiles, two CTAs per SM, mbarrier pipeline, 3 = three stages.
+  const char *env = getenv("GSB_GEMM_VARIANT");
+  switch (env ? atoi(env) : 0) {
+    case 1: return wall_gemm_launch<GemmCfg<128, 128, 16, 4, 1, false>>(ctx, a, st);
+    case 2: return wall_gemm_launch<GemmCfg<128, 64, 16, 3, 2, true>>(ctx, a, st);
+    case 3: return wall_gemm_launch<GemmCfg<128, 128, 16, 3, 1, true>>(ctx, a, st);
+    default: return wall_gemm_launch<GemmCfg<128, 128, 16, 4, 1, true>>(ctx, a, st);
   }
-  a.part = ctx->gemm_ws;
-  GSB_SMEM_OPT_IN(k_wall_gemm_sk, kSkSmem);
-  k_wall_gemm_sk<<<grid, STHREADS, kSkSmem, st>>>(a);
-  GSB_LAUNCH_CHECK();
-  if (a.spc % a.ntk != 0) {  // the runs do not end on tile boundaries: some tiles are cut
-    k_wall_reduce<<<dim3(16, n_tiles), 256, 0, st>>>(a);
-    GSB_LAUNCH_CHECK();
-  }
-  return GSB_OK;
 }
 
 int gsb_wall_scatter(gsb_ctx *ctx, const double *wall_dev, double *bc_dev, int accumulate, int batch, void *stream) {
