@@ -377,6 +377,11 @@ void sweep_fused_plan(int nz, int nr, int batch, int nst, int num_sms, int *stri
 int smooth_fused(gsb_ctx *ctx, const LevelGeom &g, double *cur, double *alt, size_t stride, const double *src,
                  size_t sstride, int batch, double omega, int n_sweeps, const int *active, cudaStream_t st,
                  double **result);
+// fused residual + full weighting, one residual evaluation per fine point (gsb_mg.cu; odd fine sizes only)
+int residual_restrict_tiled_launch(const LevelGeom &g, const double *psi, size_t pstride, const double *src,
+                                   size_t sstride, double *dc, size_t dstride, int nzc, int nrc, int roff, int ci0,
+                                   int ci1, int zero_rest, int split_out, int batch, const int *active,
+                                   cudaStream_t st);
 int jacobi_launch(const LevelGeom &g, const double *psi, const double *src, double *out, int batch,
                   const int *active, cudaStream_t st);
 int ring_save_launch(const double *f, size_t stride, double *ring, int nz, int nr, int batch,

@@ -293,6 +293,73 @@ k_residual_restrict(LevelGeom g, const double *__restrict__ psi, size_t pstride,
   }
 }
 
+// Tiled form of the same operator for odd fine widths (2^k+1 grids, every slab level): a CTA owns 8 x 32 coarse
+// points, evaluates each of the 17 x 65 fine residuals under them ONCE into shared memory (the per-point kernel
+// above evaluates every residual 2.25 times) and then applies the 9-point weights.  `roff` = fine row of coarse
+// row 0 (slab arrays carry halo rows); rows [ci0, ci1) of dc are computed, the others are zeroed if zero_rest.
+struct RRTiledArgs {
+  LevelGeom g;
+  const double *psi, *src;
+  double *dc;
+  size_t pstride, sstride, dstride;
+  int nzc, nrc, roff, ci0, ci1, row_base, zero_rest, split_out;
+  const int *active;
+};
+constexpr int kRRTI = 8, kRRTJ = 32, kRRFR = 2 * kRRTI + 1, kRRFC = 2 * kRRTJ + 1;
+__global__ void __launch_bounds__(256) k_residual_restrict_tiled(const RRTiledArgs a) {
+  __shared__ double sr[kRRFR][kRRFC + 1];
+  const int b = blockIdx.z;
+  if (a.active && !a.active[b]) return;
+  const LevelGeom &g = a.g;
+  const int J0 = blockIdx.x * kRRTJ, I0 = a.row_base + blockIdx.y * kRRTI;
+  const double *pb = a.psi + (size_t)b * a.pstride;
+  const double *sb = a.src + (size_t)b * a.sstride;
+  const int i_lo = max(I0, a.ci0), i_hi = min(I0 + kRRTI, a.ci1);  // coarse rows of this tile that are computed
+  const int iz_lo = 2 * i_lo + a.roff - 1, iz_hi = 2 * (i_hi - 1) + a.roff + 1;
+  for (int idx = threadIdx.x; idx < kRRFR * kRRFC; idx += blockDim.x) {
+    const int fr = idx / kRRFC, fc = idx - fr * kRRFC;
+    const int iz = 2 * I0 + a.roff - 1 + fr, ir = 2 * J0 - 1 + fc;
+    double v = 0.0;
+    if (i_lo < i_hi && iz >= iz_lo && iz <= iz_hi && ir >= 1 && ir <= g.nr - 2) {
+      const double *q = pb + (size_t)iz * g.nr + ir;
+      v = -dsub(gs_apply(g, ir, q[0], q[1], q[-1], q[-g.nr], q[g.nr]), sb[(size_t)iz * g.nr + ir]);
+    }
+    sr[fr][fc] = v;
+  }
+  __syncthreads();
+  const int tj = threadIdx.x & (kRRTJ - 1), ti = threadIdx.x / kRRTJ;
+  const int I = I0 + ti, J = J0 + tj;
+  if (I >= a.nzc || J >= a.nrc) return;
+  double v = 0.0;
+  const bool row_on = I >= a.ci0 && I < a.ci1;
+  if (row_on && J > 0 && J < a.nrc - 1) {
+    const int r = 2 * ti + 1, c = 2 * tj + 1;
+    v = fw9(sr[r][c], sr[r - 1][c], sr[r + 1][c], sr[r][c - 1], sr[r][c + 1], sr[r - 1][c - 1], sr[r - 1][c + 1],
+            sr[r + 1][c - 1], sr[r + 1][c + 1]);
+  } else if (!row_on && !a.zero_rest) {
+    return;
+  }
+  if (a.split_out) {
+    const int hwc = (a.nrc + 1) / 2;
+    a.dc[(size_t)b * a.dstride + ((((I + J) & 1) * a.nzc + I) * hwc + (J >> 1))] = v;
+  } else {
+    a.dc[(size_t)b * a.dstride + (size_t)I * a.nrc + J] = v;
+  }
+}
+
+int residual_restrict_tiled_launch(const LevelGeom &g, const double *psi, size_t pstride, const double *src,
+                                   size_t sstride, double *dc, size_t dstride, int nzc, int nrc, int roff, int ci0,
+                                   int ci1, int zero_rest, int split_out, int batch, const int *active,
+                                   cudaStream_t st) {
+  RRTiledArgs a{g, psi, src, dc, pstride, sstride, dstride, nzc, nrc, roff, ci0, ci1, zero_rest ? 0 : ci0, zero_rest,
+                split_out, active};
+  const int rows = zero_rest ? nzc : ci1 - ci0;
+  if (rows <= 0 || nrc <= 0) return GSB_OK;
+  k_residual_restrict_tiled<<<dim3((nrc + kRRTJ - 1) / kRRTJ, (rows + kRRTI - 1) / kRRTI, batch), 256, 0, st>>>(a);
+  GSB_LAUNCH_CHECK();
+  return GSB_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // a7  bilinear prolongation (multigrid_solve.py:102-145) incl. its slicing limits
 // ------------------------------------------------------------------------------------------
@@ -560,8 +627,16 @@ int vcycle_launch(gsb_ctx *ctx, double *psi, size_t psi_stride, const double *sr
     curv[l] = cur;
     const dim3 grd((c.nr + 31) / 32, (c.nz + 7) / 8, batch);
     const int split = (l + 1 == l0) ? 1 : 0;
-    k_residual_restrict<<<grd, blk, 0, st>>>(g, cur, XS(l), S(l), SS(l), ctx->levels[l + 1].d, c.nz, c.nr, split, active);
-    GSB_LAUNCH_CHECK();
+    if ((g.nz & 1) && (g.nr & 1) && c.nz >= 3 && c.nr >= 3 && (long long)g.nz * g.nr >= 4096) {
+      // odd sizes (coarse point (I,J) sits on fine (2I,2J)): every fine residual is evaluated once per tile
+      const size_t ds = split ? (size_t)2 * c.nz * ((c.nr + 1) / 2) : (size_t)c.nz * c.nr;
+      rc = residual_restrict_tiled_launch(g, cur, XS(l), S(l), SS(l), ctx->levels[l + 1].d, ds, c.nz, c.nr, 0, 1, c.nz - 1,
+                                          1, split, batch, active, st);
+      if (rc) return rc;
+    } else {
+      k_residual_restrict<<<grd, blk, 0, st>>>(g, cur, XS(l), S(l), SS(l), ctx->levels[l + 1].d, c.nz, c.nr, split, active);
+      GSB_LAUNCH_CHECK();
+    }
     if (l + 1 < L - 1 && l + 1 != l0)  // resident / base solve zero-initialise on chip
       GSB_CUDA(cudaMemsetAsync(ctx->levels[l + 1].e, 0, (size_t)batch * c.nz * c.nr * sizeof(double), st));
   }

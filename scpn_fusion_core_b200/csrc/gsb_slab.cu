@@ -64,19 +64,33 @@ k_slab_prolong_add(const double *__restrict__ ec, int nrc, double *__restrict__ 
 
 // max |L psi - src| over local rows [row0,row1), interior columns; out accumulates with atomicMax on
 // the bit pattern (non-negative doubles order like unsigned integers) - order independent
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 k_slab_residual_linf(LevelGeom g, const double *__restrict__ psi, const double *__restrict__ src, int row0, int row1,
                      unsigned long long *__restrict__ out) {
   __shared__ double sh[32];
   double m = 0.0;
-  const int ncol = g.nr - 2;
-  const long long total = (long long)(row1 - row0) * ncol;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int iz = row0 + (int)(i / ncol), ir = 1 + (int)(i % ncol);
-    const double *q = psi + (size_t)iz * g.nr + ir;
-    const double r = dsub(gs_apply(g, ir, q[0], q[1], q[-1], q[-g.nr], q[g.nr]), src[(size_t)iz * g.nr + ir]);
-    const double ar = fabs(r);
-    if (ar > m || isnan(ar)) m = ar;  // a NaN residual must surface (np.max propagates NaN)
+  // grid (column chunks, row bands): a thread keeps its column and walks down the rows of its band with a
+  // three-row register window (one new psi row per step, coefficient lookups once per thread, no integer division)
+  const int ir = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+  const int nb = gridDim.y, band = blockIdx.y;
+  const int z0 = row0 + (int)((long long)(row1 - row0) * band / nb), z1 = row0 + (int)((long long)(row1 - row0) * (band + 1) / nb);
+  if (ir <= g.nr - 2 && z0 < z1) {
+    const double rs = g.r_safe[ir], irs = g.inv_r_safe[ir];
+    const double *q = psi + (size_t)z0 * g.nr + ir;
+    const double *f = src + (size_t)z0 * g.nr + ir;
+    double sm = q[-g.nr], cw = q[-1], c0 = q[0], ce = q[1];
+    for (int iz = z0; iz < z1; ++iz) {
+      const double nn = q[g.nr];
+      const double r = dsub(gs_apply_v(g, rs, irs, c0, ce, cw, sm, nn), f[0]);
+      const double ar = fabs(r);
+      if (ar > m || isnan(ar)) m = ar;  // a NaN residual must surface (np.max propagates NaN)
+      q += g.nr;
+      f += g.nr;
+      sm = c0;
+      c0 = nn;
+      cw = q[-1];
+      ce = q[1];
+    }
   }
   // block_max uses fmax (drops NaN): carry a NaN flag alongside
   const int anynan = __syncthreads_or(isnan(m) ? 1 : 0);
@@ -294,10 +308,8 @@ int gsb_slab_residual_restrict(gsb_ctx *fine, const double *x_dev, const double 
   int rc = slab_plan(fine);
   if (rc) return rc;
   if (ci0 == ci1) return GSB_OK;
-  const dim3 blk(32, 8, 1), grd((nrc + 31) / 32, (ci1 - ci0 + 7) / 8, 1);
-  k_slab_residual_restrict<<<grd, blk, 0, (cudaStream_t)stream>>>(fine->levels[0].g, x_dev, src_dev, dc_dev, nrc, roff, ci0, ci1);
-  GSB_LAUNCH_CHECK();
-  return GSB_OK;
+  return residual_restrict_tiled_launch(fine->levels[0].g, x_dev, fine->n, src_dev, fine->n, dc_dev, (size_t)nzc_loc * nrc,
+                                        nzc_loc, nrc, roff, ci0, ci1, 0, 0, 1, nullptr, (cudaStream_t)stream);
 }
 
 int gsb_slab_prolong_add(gsb_ctx *fine, const double *ec_dev, int nzc_loc, int nrc, double *x_dev, int roff,
@@ -323,10 +335,10 @@ int gsb_slab_residual_linf(gsb_ctx *ctx, const double *x_dev, const double *src_
   int rc = slab_plan(ctx);
   if (rc) return rc;
   if (row0 == row1 || ctx->nr < 3) return GSB_OK;
-  const long long total = (long long)(row1 - row0) * (ctx->nr - 2);
-  const int blocks = (int)std::min<long long>((total + 255) / 256, 4LL * ctx->num_sms);
-  k_slab_residual_linf<<<blocks, 256, 0, (cudaStream_t)stream>>>(ctx->levels[0].g, x_dev, src_dev, row0, row1,
-                                                                 reinterpret_cast<unsigned long long *>(out_dev));
+  const int cchunks = (ctx->nr - 2 + 127) / 128;
+  const int bands = std::max(1, std::min(row1 - row0, (8 * ctx->num_sms + cchunks - 1) / cchunks));
+  k_slab_residual_linf<<<dim3(cchunks, bands), 128, 0, (cudaStream_t)stream>>>(ctx->levels[0].g, x_dev, src_dev, row0, row1,
+                                                                              reinterpret_cast<unsigned long long *>(out_dev));
   GSB_LAUNCH_CHECK();
   return GSB_OK;
 }

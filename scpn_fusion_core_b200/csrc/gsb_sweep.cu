@@ -206,9 +206,11 @@ void sweep_fused_plan(int nz, int nr, int batch, int nst, int num_sms, int *stri
   const long long warps = (long long)*n_strips * batch;
   const long long want = 24LL * num_sms;
   int bands = 1;
-  // a warp marches down its band row by row (~0.3 us per row step): short bands keep small levels from
-  // being latency bound; 32 rows is the floor (the 2*nst halo rows are recomputed per band)
-  if (warps < want) bands = (int)std::min<long long>((want + warps - 1) / warps, std::max(1, nz / 32));
+  // a warp marches down its band row by row, ~1 us per row step when it is alone on its SM (measured on
+  // 257^2..1025^2 single grids: 45 us per launch with 32-row bands, whatever the level): a level that cannot fill
+  // the GPU is latency bound, so its bands shrink down to 8 rows - the 2*nst halo rows recomputed per band are
+  // free there, and the results do not depend on the tiling
+  if (warps < want) bands = (int)std::min<long long>((want + warps - 1) / warps, std::max(1, nz / 8));
   const int br = (nz + bands - 1) / bands;
   *band_rows = br;
   *n_bands = (nz + br - 1) / br;

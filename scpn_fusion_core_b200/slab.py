@@ -70,11 +70,15 @@ class SlabLevel:
 
 
 def plan_slab_levels(nz: int, nr: int, r_min: float, r_max: float, z_min: float, z_max: float, world: int,
-                     rank: int, *, halo: int = 12, min_rows: int = 32, min_grid: int = 5) -> tuple[list[SlabLevel], dict]:
+                     rank: int, *, halo: int = 12, min_rows: int = 32, min_grid: int = 5,
+                     gather_nz: int = 129) -> tuple[list[SlabLevel], dict]:
     """Row partition of every distributed level plus the geometry of the first gathered level.
 
-    Needs nz = 2^p + 1 rows with (nz-1) divisible by world; a level stays distributed while it has at
-    least ``min_rows`` (and an even number of) rows per rank and the reference's recursion continues.
+    Needs nz = 2^p + 1 rows with (nz-1) divisible by world; a level stays distributed while it has more than
+    ``gather_nz`` rows in total, at least ``min_rows`` (and an even number of) rows per rank, and the
+    reference's recursion continues.  ``gather_nz`` = 129: a 129-row level and everything below it fits the
+    shared memory of one SM, so the replicated tail of the V-cycle is ONE resident-kernel launch
+    (k_vcycle_resident) instead of several latency-bound streaming levels.
     """
     if world < 1 or not (0 <= rank < world):
         raise ValueError("bad rank/world")
@@ -103,7 +107,7 @@ def plan_slab_levels(nz: int, nr: int, r_min: float, r_max: float, z_min: float,
     while True:
         rows = (nz_l - 1) // world
         stop = min_grid >= nz_l or min_grid >= nr_l  # the reference's base case (multigrid_solve.py:292)
-        if stop or rows < max(min_rows, 2 * halo) or rows % 2:
+        if stop or rows < max(min_rows, 2 * halo) or rows % 2 or (levels and nz_l <= gather_nz):
             break
         r_row, dr_l, dz_l = tables(lev)
         g0 = rank * rows
@@ -389,7 +393,8 @@ class SlabMultigrid:
 
     def __init__(self, nz: int, nr: int, r_min: float, r_max: float, z_min: float, z_max: float, comm: SlabComm,
                  ops: Any, *, halo: int | None = None, min_rows: int = 32, omega: float = 1.0, pre_smooth: int = 3,
-                 post_smooth: int = 3, min_grid: int = 5, use_graph: bool = True, strict_graph: bool = False):
+                 post_smooth: int = 3, min_grid: int = 5, use_graph: bool = True, strict_graph: bool = False,
+                 gather_nz: int = 129):
         self.use_graph, self.strict_graph, self.used_graph = use_graph, strict_graph, False
         import os as _os
         self.use_native = _os.environ.get("GSB_SLAB_NATIVE", "1") != "0"  # C driver of the distributed levels
@@ -405,7 +410,8 @@ class SlabMultigrid:
         self.comm, self.ops = comm, ops
         self.omega, self.pre, self.post, self.min_grid, self.halo = omega, pre_smooth, post_smooth, min_grid, halo
         self.levels, self.gathered = plan_slab_levels(nz, nr, r_min, r_max, z_min, z_max, comm.world, comm.rank,
-                                                      halo=halo, min_rows=min_rows, min_grid=min_grid)
+                                                      halo=halo, min_rows=min_rows, min_grid=min_grid,
+                                                      gather_nz=gather_nz)
         if not self.levels:
             raise ValueError("grid too small for a slab decomposition at this world size (use multigrid_solve)")
         self.nz, self.nr = nz, nr

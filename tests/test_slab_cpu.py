@@ -43,7 +43,7 @@ def _worker(rank, world, port, nz, nr, out_dir):
     try:
         src, bc = _problem(nz, nr)
         comm = SlabComm(rank, world)
-        mgs = SlabMultigrid(nz, nr, 4.0, 8.0, -4.0, 4.0, comm, NumpySlabOps(), min_rows=16)
+        mgs = SlabMultigrid(nz, nr, 4.0, 8.0, -4.0, 4.0, comm, NumpySlabOps(), min_rows=16, gather_nz=0)
         g0, g1 = mgs.owned_rows()
         psi, res, n, conv = mgs.solve(src[g0:g1], bc[g0:g1], tol=1e-9, max_cycles=30)
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), psi=psi.numpy(), res=res, n=n, conv=conv, g0=g0, g1=g1,
@@ -78,7 +78,7 @@ def test_slab_world_one_and_plan():
     rg = np.tile(np.linspace(4.0, 8.0, nr), (nz, 1))
     a = rb_sor_smooth_offset(bc.copy(), src, rg, 0.0625, 0.125, 1.3, 2, 0)
     np.testing.assert_array_equal(a, G.rb_sor_smooth(bc.copy(), src, rg, 0.0625, 0.125, 1.3, 2))
-    mgs = SlabMultigrid(nz, nr, 4.0, 8.0, -4.0, 4.0, SlabComm(0, 1), NumpySlabOps(), min_rows=16)
+    mgs = SlabMultigrid(nz, nr, 4.0, 8.0, -4.0, 4.0, SlabComm(0, 1), NumpySlabOps(), min_rows=16, gather_nz=0)
     psi, res, n, conv = mgs.solve(src, bc, tol=1e-9, max_cycles=30)
     p0, r0, n0, c0 = G.mg_solve(src, bc, 4.0, 8.0, -4.0, 4.0, nr, nz, tol=1e-9, max_cycles=30)
     np.testing.assert_array_equal(psi.numpy(), p0)
