@@ -170,6 +170,9 @@ typedef struct gsb_picard_params {
   int seed;                    /* 1: Gaussian seed + 50 Jacobi (_seed_plasma) */
   int check_every;             /* host polls the active count every this many iterations */
   gsb_profile prof;
+  int external_profile;        /* 1: external_profile_mode (fusion_kernel_newton_solver.py:509) - J_phi is NOT updated
+                                  from psi inside the loop; every iteration solves with the source left by the seed
+                                  (_seed_plasma overwrites J_phi before the loop, also in this mode) */
 } gsb_picard_params;
 
 /* a13+a14: batched Picard solve (solve_equilibrium, fusion_kernel_newton_solver.py:390-615).

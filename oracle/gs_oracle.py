@@ -591,7 +591,7 @@ def anderson_mix(psi_hist, res_hist, m=5):
 
 
 def picard_solve(prob: PicardProblem, *, preserve_initial_state=False, boundary_flux=None,
-                 trace=None) -> dict[str, Any]:
+                 trace=None, external_profile=False) -> dict[str, Any]:
     """fusion_kernel_newton_solver.py:390-615 (methods multigrid/sor/jacobi/anderson; no newton).
 
     ``trace`` (a list) receives per-iteration dicts of intermediates for tests.
@@ -668,8 +668,9 @@ def picard_solve(prob: PicardProblem, *, preserve_initial_state=False, boundary_
                                cfg["dimensions"]["Z_min"], saddle=saddle)
         if abs(p_ax - p_b) < 0.1:
             p_b = p_ax * 0.1
-        prob.J_phi = plasma_source(prob.Psi, prob.RR, prob.dR, prob.dZ, p_ax, p_b, mu0, ip,
-                                   hmode=prob.hmode, ped_p=prob.ped_p, ped_ff=prob.ped_ff)
+        if not external_profile:  # external_profile_mode keeps the seed's J_phi (fusion_kernel_newton_solver.py:509)
+            prob.J_phi = plasma_source(prob.Psi, prob.RR, prob.dR, prob.dZ, p_ax, p_b, mu0, ip,
+                                       hmode=prob.hmode, ped_p=prob.ped_p, ped_ff=prob.ped_ff)
         src = -mu0 * prob.RR * prob.J_phi
         last_src = src
         if method == "jacobi":

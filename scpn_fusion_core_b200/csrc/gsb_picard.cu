@@ -717,7 +717,7 @@ struct PicardResArgs {
   const double *seedJ, *cf, *mr, *rrow;
   const int *rowmask;
   double seed_sum_drdz;
-  int batch, max_iter, seed, saddle, need_gs;
+  int batch, max_iter, seed, saddle, need_gs, external;
   double tol, gs_tol, alpha, oma, omega;
   double dr, dz, dr2, dz2, four_drdz;
   GradGeom gg;
@@ -954,6 +954,12 @@ k_picard_resident(const __grid_constant__ RPlan plan, const __grid_constant__ Pi
       }
       // 50 swaps: colour 0 is back in its home plane
     }
+    if (a.external && !do_seed) {  // no seed ran: the loop's source is identically zero (J_phi = 0)
+      for (int i = tid; i < planes; i += T) {
+        wj[i] = 0.0;
+        wsrc[i] = 0.0;
+      }
+    }
     // current iterate -> workspace slot `cur`
     __syncthreads();
     for (int i = tid; i < planes; i += T) wpsi[(size_t)cur * planes + i] = res_pool[xo + i];
@@ -1087,6 +1093,7 @@ k_picard_resident(const __grid_constant__ RPlan plan, const __grid_constant__ Pi
       __syncthreads();
       GSB_PHASE(48);  // topology
 
+      if (!a.external) {  // external_profile_mode keeps the seed's J_phi / source (newton_solver.py:509)
       // ---- S1: J_raw(psi) + deterministic block sum (a12)
       double denom = dsub(psi_b, psi_ax);
       if (fabs(denom) < 1e-9) denom = 1e-9;
@@ -1162,6 +1169,7 @@ k_picard_resident(const __grid_constant__ RPlan plan, const __grid_constant__ Pi
           }
         }
       }
+      }  // !external
       __syncthreads();
       GSB_PHASE(49);  // source
 
@@ -1704,6 +1712,7 @@ static int picard_resident_launch(gsb_ctx *ctx, const gsb_picard_params *p, doub
   a.seed = p->seed;
   a.saddle = p->saddle;
   a.need_gs = p->require_gs_residual;
+  a.external = p->external_profile;
   a.tol = p->tol;
   a.gs_tol = p->gs_tol;
   a.alpha = p->alpha;
@@ -1862,6 +1871,11 @@ static int picard_solve_impl(gsb_ctx *ctx, const gsb_picard_params *p, double *p
   GSB_LAUNCH_CHECK();
   rc = ring_save_launch(bc_dev, n, w->ring, nz, nr, batch, st);
   if (rc) return rc;
+  if (p->external_profile) {  // equilibria whose seed does not run keep J_phi = 0 and a zero source
+    GSB_REQUIRE(mask_dev == nullptr, "external_profile_mode is not combined with a masked (free-boundary batch) solve");
+    GSB_CUDA(cudaMemsetAsync(jphi_dev, 0, (size_t)batch * n * sizeof(double), st));
+    GSB_CUDA(cudaMemsetAsync(w->source, 0, (size_t)batch * n * sizeof(double), st));
+  }
   if (p->seed) {
     // Psi_best = Psi.copy() is taken BEFORE seeding (newton_solver.py:484,496)
     GSB_CUDA(cudaMemcpyAsync(w->buf2, psi_dev, (size_t)batch * n * sizeof(double), cudaMemcpyDeviceToDevice, st));
@@ -1891,12 +1905,14 @@ static int picard_solve_impl(gsb_ctx *ctx, const gsb_picard_params *p, double *p
     k_topo_final<<<(batch + 127) / 128, 128, 0, st>>>(bufs, s.cur, n, nr, P, w->tpart, p->saddle ? s.xsel : nullptr,
                                                       s.topo, s.axbnd, 1, batch, s.active);
     GSB_LAUNCH_CHECK();
-    k_source_raw<<<dim3(P, batch), 256, 0, st>>>(bufs, s.cur, n, nz, nr, s.axbnd, prof, prof_dev, ctx->r_dev, w->cf,
-                                                 jphi_dev, w->spart, s.active);
-    GSB_LAUNCH_CHECK();
-    k_source_scale<<<dim3(P, batch), 256, 0, st>>>(n, nz, nr, ctx->dr, ctx->dz, ip_dev, w->spart, P, w->mr, jphi_dev,
-                                                   w->source, s.scale, s.active);
-    GSB_LAUNCH_CHECK();
+    if (!p->external_profile) {
+      k_source_raw<<<dim3(P, batch), 256, 0, st>>>(bufs, s.cur, n, nz, nr, s.axbnd, prof, prof_dev, ctx->r_dev, w->cf,
+                                                   jphi_dev, w->spart, s.active);
+      GSB_LAUNCH_CHECK();
+      k_source_scale<<<dim3(P, batch), 256, 0, st>>>(n, nz, nr, ctx->dr, ctx->dz, ip_dev, w->spart, P, w->mr, jphi_dev,
+                                                     w->source, s.scale, s.active);
+      GSB_LAUNCH_CHECK();
+    }
     if (p->method == 0) {
       k_copy_from_cur<<<dim3(copy_blocks, batch), 256, 0, st>>>(bufs, s.cur, n, w->W, 0, s.active);
       GSB_LAUNCH_CHECK();

@@ -191,6 +191,7 @@ class _GridMixin:
         p.seed = 1
         p.check_every = int(so.get("gpu_check_every", 8))
         p.prof = _profile_struct(self._hmode, self.ped_params_p, self.ped_params_ff)
+        p.external_profile = 1 if bool(getattr(self, "external_profile_mode", False)) else 0
         return p
 
     # Green's tables are geometry-only: build once per (coil set, flavour)
@@ -271,12 +272,23 @@ class FusionKernel(FreeBoundaryMixin, _GridMixin):
     def find_x_point(self, Psi):
         """fusion_kernel.py:255-340: ``((R_x, Z_x), Psi_x)``."""
         raw = np.asarray(Psi, dtype=np.float64)
-        if not np.isfinite(raw).all():
-            raise NotImplementedError("find_x_point on non-finite flux is outside the B200 hot path")
-        t = self._topology(raw)
+        fin = np.isfinite(raw)
+        if fin.all():
+            t = self._topology(raw)
+            if t[6] == 0.0:
+                return (0.0, 0.0), float(t[7])
+            return (float(self.R[int(t[4])]), float(self.Z[int(t[3])])), float(t[5])
+        # non-finite entries (:269-273): the search runs on nan_to_num(psi); the reported flux is the raw value
+        # at the chosen point when that is finite, else the sanitised one; the fallback is the finite minimum
+        if not fin.any():
+            return (0.0, 0.0), 0.0
+        safe = np.nan_to_num(raw, nan=0.0, posinf=1e300, neginf=-1e300)
+        t = self._topology(safe)
         if t[6] == 0.0:
-            return (0.0, 0.0), float(t[7])
-        return (float(self.R[int(t[4])]), float(self.Z[int(t[3])])), float(t[5])
+            return (0.0, 0.0), float(np.min(raw[fin]))
+        iz, ir = int(t[3]), int(t[4])
+        px = float(raw[iz, ir]) if np.isfinite(raw[iz, ir]) else float(safe[iz, ir])
+        return (float(self.R[ir]), float(self.Z[iz])), px
 
     def _find_magnetic_axis(self):
         """fusion_kernel.py:342-355: ``(iz, ir, Psi_axis)``."""
@@ -373,8 +385,6 @@ class FusionKernel(FreeBoundaryMixin, _GridMixin):
         """fusion_kernel_newton_solver.py:390-615 (Picard loop on the device)."""
         t0 = time.time()
         method = self.cfg["solver"].get("solver_method", "multigrid")
-        if getattr(self, "external_profile_mode", False):
-            raise NotImplementedError("external_profile_mode is outside the B200 hot path")
         params = self._picard_params()
         ip_target = float(self.cfg["physics"]["plasma_current_target"])
         if abs(ip_target) < 1e-12 and not preserve_initial_state:

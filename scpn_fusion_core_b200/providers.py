@@ -176,9 +176,26 @@ def multigrid_vcycle(source: Any, psi_bc: Any, r_min: float, r_max: float, z_min
     return _gpu_multigrid_solve(source, psi_bc, r_min, r_max, z_min, z_max, int(nr), int(nz), tol=tol, max_cycles=int(max_cycles))
 
 
-def register(multi: Any) -> None:
-    """Register the GPU tier into the reference's registry module (``_multi_compat``)."""
+def register(multi: Any, replace: bool = True) -> None:
+    """Register the GPU tier into the reference's registry module (``_multi_compat``).
+
+    The reference already registers its own wgpu provider for ``gs_rb_sor_smooth`` at ``BackendTier.GPU``
+    (``_multi_compat_providers.py:828-847``); entries of one tier keep their registration order, so with
+    ``replace`` (default) that entry is dropped first - both cannot serve the same tier, and the wgpu one needs the
+    ``scpn_fusion_rs`` wheel this package stands in for.
+    """
     tier = multi.BackendTier.GPU
+    if replace:
+        with multi._registry_lock:
+            for name in ("gs_rb_sor_smooth", "multigrid_solve"):
+                if name in multi._registry:
+                    multi._registry[name] = [(t, f) for t, f in multi._registry[name] if t != tier]
+                multi._dispatch_cache.pop(name, None)
+        reg = getattr(multi, "_class_registry", None)
+        if reg is not None and "equilibrium_kernel" in reg:
+            with multi._class_registry_lock:
+                reg["equilibrium_kernel"] = [(t, f) for t, f in reg["equilibrium_kernel"] if t != tier]
+                multi._class_dispatch_cache.pop("equilibrium_kernel", None)
     multi.register_kernel("gs_rb_sor_smooth", tier, _gpu_gs_rb_sor_smooth)
     multi.register_kernel("multigrid_solve", tier, _gpu_multigrid_solve)
     multi.register_kernel_class("equilibrium_kernel", tier, _gpu_equilibrium_kernel_loader)

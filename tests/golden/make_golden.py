@@ -545,6 +545,24 @@ def gen_hpc():
     _save("hpc_solver", **out)
 
 
+def gen_external():
+    """external_profile_mode (the transport-coupling caller, _integrated_transport_solver_init.py:28): the Picard
+    loop does not update J_phi from psi (fusion_kernel_newton_solver.py:509); _seed_plasma still overwrites it."""
+    out = {}
+    for tag, name, n in (("iter65x", "iter_config.json", 65), ("iterval33x", "iter_validated_config.json", 33)):
+        cfg = _cfg(name, n)
+        k = _kernel(cfg)
+        k.external_profile_mode = True
+        k.J_phi = np.ones_like(k.Psi)  # what the external caller put there; the seed replaces it
+        r = k.solve_equilibrium()
+        out[tag + "_cfg"] = np.array(json.dumps(cfg))
+        out[tag + "_psi"], out[tag + "_jphi"] = k.Psi, k.J_phi
+        out[tag + "_meta"] = np.array([r["iterations"], float(r["converged"]), r["residual"], r["gs_residual"]])
+        out[tag + "_hist"] = np.array(r["residual_history"])
+        print(" ", tag, r["iterations"], r["converged"], r["residual"])
+    _save("solve_external", **out)
+
+
 def gen_mg_4097():
     """BASELINE configs[4] / SURVEY.md 8d config 5: the reference's multigrid_solve on the 4097^2 bench problem
     (bench_gpu_gs_solver._problem source, psi_bc = 0, tol 1e-8, omega 1.0, 3/3, min_grid 5; 13 levels).  Run once

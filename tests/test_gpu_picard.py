@@ -219,6 +219,45 @@ def test_divergence_reverts_to_best_state_or_raises(pkg):
         k.solve_equilibrium(preserve_initial_state=True, boundary_flux=bad)
 
 
+def test_external_profile_mode_and_nonfinite_x_point(pkg):
+    """The transport-coupling caller's mode (external_profile_mode, newton_solver.py:509) on the resident kernel and on
+    the streaming loop, against the reference fixture; find_x_point on non-finite flux (fusion_kernel.py:269-273)."""
+    import os
+    z = golden("solve_external")
+    for tag in ("iter65x", "iterval33x"):
+        for streaming in (False, True):
+            k = _kernel(pkg, golden_cfg(z, tag))
+            k.external_profile_mode = True
+            k.J_phi = np.ones_like(k.Psi)
+            if streaming:
+                os.environ["GSB_PICARD_STREAMING"] = "1"
+            try:
+                r = k.solve_equilibrium()
+            finally:
+                os.environ.pop("GSB_PICARD_STREAMING", None)
+            meta = z[tag + "_meta"]
+            assert abs(r["iterations"] - int(meta[0])) <= 1 and r["converged"] == bool(meta[1])
+            assert rel_l2(r["psi"], z[tag + "_psi"]) <= PSI_TOL
+            assert rel_l2(k.J_phi, z[tag + "_jphi"]) <= 1e-12
+            n = min(len(r["residual_history"]), len(z[tag + "_hist"]))
+            np.testing.assert_allclose(r["residual_history"][:n], z[tag + "_hist"][:n], rtol=1e-7)
+    # non-finite flux maps: same answers as the oracle (nan_to_num search, raw value reported when finite)
+    zz, k = _pieces_kernel(pkg)
+    rng = np.random.default_rng(5)
+    for saddle in (False, True):
+        k.cfg["solver"]["xpoint_use_saddle_detection"] = saddle
+        for trial in range(4):
+            psi = zz["psi"].copy()
+            bad = rng.integers(0, psi.size, size=6)
+            psi.reshape(-1)[bad[:2]] = np.nan
+            psi.reshape(-1)[bad[2:4]] = np.inf
+            psi.reshape(-1)[bad[4:]] = -np.inf
+            got = k.find_x_point(psi)
+            want = G.find_x_point(psi, k.R, k.Z, k.dR, k.dZ, k.cfg["dimensions"]["Z_min"], saddle=saddle)
+            assert got == want
+    assert k.find_x_point(np.full_like(zz["psi"], np.nan)) == ((0.0, 0.0), 0.0)
+
+
 def test_unsupported_methods_are_loud(pkg):
     z = golden("solves")
     for m in ("newton", "anderson", "rust_multigrid"):

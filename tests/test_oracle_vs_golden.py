@@ -339,3 +339,17 @@ def test_lane_c_wall_matrix_agrees_with_the_pinned_lane_a_green_function():
     g1 = G.greens_psi_si(1.7, 0.4, 2.3, -0.6)
     g2 = G.greens_psi_si(2.3, -0.6, 1.7, 0.4)
     assert abs(g1 - g2) <= 1e-15 * abs(g1)
+
+
+def test_external_profile_mode_matches_reference():
+    """external_profile_mode (fusion_kernel_newton_solver.py:509): J_phi stays what _seed_plasma left."""
+    z = golden("solve_external")
+    for tag in ("iter65x", "iterval33x"):
+        prob = G.PicardProblem(golden_cfg(z, tag))
+        prob.J_phi = np.ones_like(prob.Psi)
+        r = G.picard_solve(prob, external_profile=True)
+        meta = z[tag + "_meta"]
+        assert r["iterations"] == int(meta[0]) and r["converged"] == bool(meta[1])
+        assert rel_l2(r["psi"], z[tag + "_psi"]) <= 1e-13
+        assert rel_l2(prob.J_phi, z[tag + "_jphi"]) <= 1e-13
+        np.testing.assert_allclose(r["residual_history"], z[tag + "_hist"], rtol=1e-10)
