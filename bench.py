@@ -47,9 +47,11 @@ GRID = 129
 COIL_SCALE = 1.0e6  # config currents are MA; the reference's SI-mu0 coil flux wants amperes (tests/golden/make_golden.py)
 # Measured constants of the dominant kernel from this round's committed ncu --set full capture (profiles/);
 # None until a capture of the current kernel exists.
-TRAFFIC_NCU = None            # dram__bytes_read.sum + dram__bytes_write.sum per launch at the headline configuration
-DP_WARP_INSTR_PER_ITER = None  # smsp__inst_executed_pipe_fp64.sum / Picard iterations (warp instructions)
-NCU_SOURCE = None
+# r2 capture (profiles/r2_picard_resident.md): ncu --set full of ONE k_picard_resident launch = one 4096-sample
+# fixed-boundary sweep, 367 540 Picard iterations: DRAM 20.55 GB read + 116.23 GB written, FP64 pipe 26.2 % active.
+TRAFFIC_NCU_PER_ITER = 136.78e9 / 367540.0   # DRAM bytes per Picard iteration (workspace write-back dominates)
+DP_WARP_INSTR_PER_ITER = 149.6e3             # FP64 warp instructions per Picard iteration (pipe-active cycles x 4 / 2)
+NCU_SOURCE = "profiles/r2_picard_resident.md"
 ITER_COILS = [(3.5, 3.0, -1.0), (8.0, 3.0, 4.0), (9.5, 0.0, 6.0), (8.0, -3.0, 4.0), (3.5, -3.0, -1.0),
               (9.5, 3.0, 3.0), (2.1, 0.0, 0.0)]
 PSI_TOL = 1e-9
@@ -322,7 +324,11 @@ def run_gpu_arm(args) -> None:
     total = args.batch if args.scaling == "strong" else world * args.batch
     cfg = base_config(args.grid)
     bk = pkg.BatchedFusionKernel(cfg, device=local)
-    cc, ip, ped = uq_inputs(B, 2026 + lo)  # sample k of the whole job is seeded 2026 + k on every rank layout
+    # strong scaling: sample k of the ONE sweep is seeded 2026 + k whatever the rank layout.  Weak scaling: every GPU
+    # solves the named 4096-sample sweep (seeds 2026 .. 2026 + B - 1), so per-GPU work is identical by construction and
+    # a straggler (one sample in ~8000 of a longer seed range does not converge within 500 Picard iterations and keeps
+    # a single SM busy for every remaining outer iteration) cannot masquerade as a scaling loss.
+    cc, ip, ped = uq_inputs(B, 2026 + (lo if args.scaling == "strong" else 0))
     ped8 = np.concatenate([ped, ped], axis=1)
     mu0 = cfg["physics"]["vacuum_permeability"]
     w_fixed = (mu0 * cc) / (2.0 * np.pi)      # calculate_vacuum_field weights (fusion_kernel.py:245-249)
@@ -410,7 +416,9 @@ def run_gpu_arm(args) -> None:
             "kernel": "k_picard_resident (persistent: one CTA per equilibrium, psi resident in shared memory for the "
                       "whole inner solve)" if resident else "streaming Picard launch sequence (grid does not fit one SM)",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-            "traffic": (TRAFFIC_NCU / k_launches if (TRAFFIC_NCU and resident) else None), "traffic_source": NCU_SOURCE,
+            "traffic": (TRAFFIC_NCU_PER_ITER * it_sum / max(k_launches, 1.0) if resident else None),
+            "traffic_source": NCU_SOURCE + " (ncu dram__bytes_read.sum + dram__bytes_write.sum per Picard iteration x the "
+                              "live iteration count, per launch)",
             "launch_ms": k_ms_total / max(k_launches, 1.0), "launches_per_step": k_launches,
             "algorithmic_bytes_per_launch": alg_bytes / max(k_launches, 1.0),
             "algorithmic_bytes_note": f"{BYTES_PER_POINT_ITER:.0f} B per grid point per Picard iteration x {n_pts} points x "
@@ -418,7 +426,7 @@ def run_gpu_arm(args) -> None:
                                       "iterations); psi never leaves shared memory during an inner solve, so frac may "
                                       "exceed 1 - the kernel is FP64-issue bound, not HBM bound: see fp64",
             "share_of_step": k_ms_total / (ms / args.steps)}
-    if DP_WARP_INSTR_PER_ITER and resident and clocks.get("sm_mhz"):
+    if resident and clocks.get("sm_mhz"):
         dp_rate = DP_WARP_INSTR_PER_ITER * 32.0 * it_sum / (k_ms_total * 1e-3)          # FP64 thread instructions / s
         dp_peak = ctx_num_sms(torch, local) * 64.0 * clocks["sm_mhz"] * 1e6             # 64 FP64 lanes / SM / clk
         roof["fp64"] = {"achieved": dp_rate / 1e12, "peak": dp_peak / 1e12, "unit": "T FP64 instr/s (DADD/DMUL/DFMA issue)",
