@@ -577,6 +577,8 @@ def run_slab(args) -> None:
     peer = False
     if world > 1 and not args.slab_nccl:
         peer = comm.enable_peer_halo(local, mgs.halo * n)
+        if peer and not args.slab_nccl_gather:
+            comm.enable_peer_gather(local, mgs.gathered["nz"] * mgs.gathered["nr"])
     g0, g1 = mgs.owned_rows()
     z = torch.linspace(-4.0, 4.0, n, dtype=torch.float64, device=f"cuda:{local}")[g0:g1, None]
     r = torch.linspace(4.0, 8.0, n, dtype=torch.float64, device=f"cuda:{local}")[None, :]
@@ -608,6 +610,8 @@ def run_slab(args) -> None:
                            "converged": bool(conv), "residual_linf": float(res),
                            "halo_transport": "NVLink peer memory (gsb_halo_push/recv, CUDA IPC)" if peer else
                                              ("NCCL point-to-point" if world > 1 else "none"),
+                           "coarse_gather": ("NVLink peer memory (gsb_gather_push/wait)" if comm.gather is not None else
+                                             ("NCCL all-gather" if world > 1 else "none")),
                            "cuda_graph": bool(mgs.used_graph), "l2_policy": f"{n * n * 8 / 2 ** 20:.0f} MiB per field exceeds L2"},
                 "ms_per_vcycle": per_cycle_ms, "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "kernel": "one multigrid V-cycle, all levels (k_sweep_warp<6>, "
@@ -620,6 +624,7 @@ def run_slab(args) -> None:
                                "every cycle (inside the timed region)"},
                 "clocks": sampler.summary()}
         print(json.dumps(line), flush=True)
+    comm.disable_peer_gather()
     if peer:
         comm.disable_peer_halo()
     dd.close()
@@ -638,6 +643,7 @@ def main() -> None:
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the plasma-wall / fixed-boundary / smoother legs")
     ap.add_argument("--slab-nccl", action="store_true", help="slab workload: NCCL point-to-point halos instead of peer memory")
+    ap.add_argument("--slab-nccl-gather", action="store_true", help="slab workload: NCCL all-gather of the coarse level (no multi-rank graph)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -301,6 +301,18 @@ int gsb_halo_recv(double *halo_up, double *halo_dn, long long n, const double *i
                   long long *flags_local, long long *flags_up, long long *flags_dn, int *counters, long long *epochs,
                   void *stream);
 
+/* Coarse-level gather over NVLink peer memory (replaces the NCCL all-gather inside a slab V-cycle, so that the cycle
+ * holds this library's kernels only and replays from a CUDA graph on every rank).  Every rank owns an IPC block
+ * {world int64 flags | two halves of buf_doubles doubles}; peer_bufs[p] / peer_flags[p] are rank p's halves / flags as
+ * mapped here (own rank included).  gsb_gather_push stores `n` doubles (this rank's owned rows) at offset `off` of the
+ * current half of every rank and raises flag[rank] there; gsb_gather_wait waits for all `world` flags, copies the
+ * assembled n_total doubles into out_dev and bumps *epoch (device counter of completed gathers, zeroed once;
+ * counters: `world` zeroed ints). */
+int gsb_gather_push(const double *rows_dev, long long n, long long off, long long buf_doubles, void *const *peer_bufs,
+                    void *const *peer_flags, int world, int rank, int *counters, const long long *epoch, void *stream);
+int gsb_gather_wait(const double *buf_local, long long buf_doubles, const long long *flags_local, int world,
+                    long long n_total, double *out_dev, long long *epoch, void *stream);
+
 /* Native driver of the distributed levels of one slab V-cycle: every launch of the descent
  * (gsb_slab_down) and of the ascent (gsb_slab_up) is issued from one call; the host gathers the
  * coarsest distributed right-hand side and runs the replicated coarse V-cycle in between.  Together they

@@ -293,6 +293,8 @@ void gsb_destroy(gsb_ctx *ctx) {
   if (ctx->mg_bc) cudaFree(ctx->mg_bc);
   if (ctx->split_src) cudaFree(ctx->split_src);
   if (ctx->x_alt) cudaFree(ctx->x_alt);
+  if (ctx->gstream) cudaStreamDestroy(ctx->gstream);
+  if (ctx->gevent) cudaEventDestroy(ctx->gevent);
   if (ctx->gemm_ws) cudaFree(ctx->gemm_ws);
   if (ctx->fb_old) cudaFree(ctx->fb_old);
   if (ctx->fb_part) cudaFree(ctx->fb_part);

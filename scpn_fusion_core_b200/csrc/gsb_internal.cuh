@@ -345,6 +345,8 @@ struct gsb_ctx {
   double *mg_bc = nullptr;  // wall ring copy for mg_solve [batch_cap][ring]
   gsb_picard_ws *picard = nullptr;
   int picard_last_iters = 0;
+  cudaStream_t gstream = nullptr;  // private capture-capable stream of the streaming Picard loop
+  cudaEvent_t gevent = nullptr;
   // optional per-kernel-class timing of gsb_free_boundary_solve (gsb_timing): CUDA events on the launching stream
   bool timing = false;
   double timing_acc[4] = {0, 0, 0, 0};  // inner Picard solves: ms, count; wall GEMMs: ms, count

@@ -1867,6 +1867,22 @@ static int picard_solve_impl(gsb_ctx *ctx, const gsb_picard_params *p, double *p
   const int copy_blocks = (int)std::min<size_t>((n + 255) / 256, 64);
   const ProfileDev prof = to_dev(p->prof);
 
+  // The loop below is ~12 launches per Picard iteration and a single equilibrium is launch-latency bound on it
+  // (257^2: 22 us per launch), so blocks of `check_every` iterations are replayed from a CUDA graph.  Graph
+  // capture is not allowed on the legacy default stream (what torch hands over by default): the whole solve runs
+  // on a private non-blocking stream ordered after / before the caller's stream by events.
+  const bool use_graph = !std::getenv("GSB_NO_GRAPH");
+  cudaStream_t caller = st;
+  if (use_graph) {
+    if (!ctx->gstream) {
+      GSB_CUDA(cudaStreamCreateWithFlags(&ctx->gstream, cudaStreamNonBlocking));
+      GSB_CUDA(cudaEventCreateWithFlags(&ctx->gevent, cudaEventDisableTiming));
+    }
+    GSB_CUDA(cudaEventRecord(ctx->gevent, caller));
+    GSB_CUDA(cudaStreamWaitEvent(ctx->gstream, ctx->gevent, 0));
+    st = ctx->gstream;
+  }
+
   k_picard_init<<<(batch + 127) / 128, 128, 0, st>>>(s, batch, p->seed ? 2 : 0, ip_dev, p->seed, mask_dev);
   GSB_LAUNCH_CHECK();
   rc = ring_save_launch(bc_dev, n, w->ring, nz, nr, batch, st);
@@ -1894,13 +1910,14 @@ static int picard_solve_impl(gsb_ctx *ctx, const gsb_picard_params *p, double *p
   const double oma = 1.0 - p->alpha;
   const int check_every = p->check_every > 0 ? p->check_every : 8;
   volatile double dr2 = ctx->dr * ctx->dr, dz2 = ctx->dz * ctx->dz, f1 = 4.0 * ctx->dr, f2 = f1 * ctx->dz;
-  int k = 0;
-  for (; k < p->max_iterations; ++k) {
+  // one Picard iteration of every active equilibrium; `poll`: reset the active counter before the decision and
+  // copy it to the host afterwards.  Nothing in here depends on the host-side iteration number.
+  auto issue_iteration = [&](bool poll) -> int {
     k_topo<<<dim3(P, batch), 256, 0, st>>>(bufs, s.cur, n, nz, nr, gg, w->rowmask, w->tpart, s.active);
     GSB_LAUNCH_CHECK();
     if (p->saddle) {
-      rc = saddle_launch(ctx, bufs, s.cur, batch, gg, dr2, dz2, f2, s.xsel, s.active, st);
-      if (rc) return rc;
+      int r2 = saddle_launch(ctx, bufs, s.cur, batch, gg, dr2, dz2, f2, s.xsel, s.active, st);
+      if (r2) return r2;
     }
     k_topo_final<<<(batch + 127) / 128, 128, 0, st>>>(bufs, s.cur, n, nr, P, w->tpart, p->saddle ? s.xsel : nullptr,
                                                       s.topo, s.axbnd, 1, batch, s.active);
@@ -1916,13 +1933,13 @@ static int picard_solve_impl(gsb_ctx *ctx, const gsb_picard_params *p, double *p
     if (p->method == 0) {
       k_copy_from_cur<<<dim3(copy_blocks, batch), 256, 0, st>>>(bufs, s.cur, n, w->W, 0, s.active);
       GSB_LAUNCH_CHECK();
-      rc = vcycle_launch(ctx, w->W, n, w->source, batch, p->omega, 3, 3, s.active, st);
-      if (rc) return rc;
+      int r2 = vcycle_launch(ctx, w->W, n, w->source, batch, p->omega, 3, 3, s.active, st);
+      if (r2) return r2;
     } else if (p->method == 1) {
       k_copy_from_cur<<<dim3(copy_blocks, batch), 256, 0, st>>>(bufs, s.cur, n, w->W, 1, s.active);
       GSB_LAUNCH_CHECK();
-      rc = smooth_launch(g, w->W, n, w->source, n, batch, p->omega, 1, 1, s.active, st);
-      if (rc) return rc;
+      int r2 = smooth_launch(g, w->W, n, w->source, n, batch, p->omega, 1, 1, s.active, st);
+      if (r2) return r2;
     } else {
       const dim3 blk(32, 8, 1), grd((nr + 31) / 32, (nz + 7) / 8, batch);
       k_jacobi_from_cur<<<grd, blk, 0, st>>>(g, bufs, s.cur, w->source, w->W, s.active);
@@ -1930,24 +1947,74 @@ static int picard_solve_impl(gsb_ctx *ctx, const gsb_picard_params *p, double *p
     }
     k_relax<<<dim3(P, batch), 256, 0, st>>>(g, bufs, s.cur, s.nxt, w->W, w->ring, w->source, p->alpha, oma, w->rpart, s.active);
     GSB_LAUNCH_CHECK();
-    const bool poll = ((k + 1) % check_every == 0) || (k + 1 == p->max_iterations);
     if (poll) GSB_CUDA(cudaMemsetAsync(ctx->counter, 0, sizeof(int), st));
     k_decide<<<(batch + 127) / 128, 128, 0, st>>>(s, w->rpart, P, (double)n, (double)(nz - 2) * (double)(nr - 2), p->tol,
                                                   p->require_gs_residual, p->gs_tol, p->max_iterations, hist_dev,
                                                   gs_hist_dev, ctx->counter, batch);
     GSB_LAUNCH_CHECK();
+    if (poll) GSB_CUDA(cudaMemcpyAsync(ctx->h_counter, ctx->counter, sizeof(int), cudaMemcpyDeviceToHost, st));
+    return GSB_OK;
+  };
+  int k = 0;
+  bool done = false;
+  // first block eagerly: it performs every lazy allocation / attribute opt-in of the sequence (none is allowed
+  // while a stream is being captured)
+  while (k < p->max_iterations && !done) {
+    const bool poll = ((k + 1) % check_every == 0) || (k + 1 == p->max_iterations);
+    rc = issue_iteration(poll);
+    if (rc) return rc;
+    ++k;
     if (poll) {
-      GSB_CUDA(cudaMemcpyAsync(ctx->h_counter, ctx->counter, sizeof(int), cudaMemcpyDeviceToHost, st));
       GSB_CUDA(cudaStreamSynchronize(st));
-      if (ctx->h_counter[0] == 0) {
-        ++k;
-        break;
+      done = ctx->h_counter[0] == 0;
+      break;
+    }
+  }
+  if (use_graph && !done && k < p->max_iterations) {
+    // later blocks: one graph of `check_every` iterations.  An equilibrium that reaches max_iterations inside a
+    // block simply turns inactive (k_decide), so whole blocks are always safe to replay.
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    const long long l0 = g_launches.load();
+    GSB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    for (int j = 0; j < check_every && rc == GSB_OK; ++j) rc = issue_iteration(j + 1 == check_every);
+    cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    const long long per_block = g_launches.load() - l0;
+    if (rc == GSB_OK && ce == cudaSuccess) ce = cudaGraphInstantiate(&exec, graph, 0);
+    if (graph) cudaGraphDestroy(graph);
+    if (rc) return rc;
+    GSB_CUDA(ce);
+    g_launches.fetch_sub(per_block);  // the captured launches did not run
+    while (k < p->max_iterations && !done) {
+      ce = cudaGraphLaunch(exec, st);
+      if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+      if (ce != cudaSuccess) break;
+      g_launches.fetch_add(per_block);
+      k += check_every;
+      done = ctx->h_counter[0] == 0;
+    }
+    cudaGraphExecDestroy(exec);
+    GSB_CUDA(ce);
+    if (k > p->max_iterations) k = p->max_iterations;
+  } else {
+    while (k < p->max_iterations && !done) {
+      const bool poll = ((k + 1) % check_every == 0) || (k + 1 == p->max_iterations);
+      rc = issue_iteration(poll);
+      if (rc) return rc;
+      ++k;
+      if (poll) {
+        GSB_CUDA(cudaStreamSynchronize(st));
+        done = ctx->h_counter[0] == 0;
       }
     }
   }
   ctx->picard_last_iters = k;
   k_finalize<<<dim3(copy_blocks, batch), 256, 0, st>>>(bufs, s, n, summary_dev, batch, mask_dev);
   GSB_LAUNCH_CHECK();
+  if (use_graph) {  // the caller's stream continues after the private one
+    GSB_CUDA(cudaEventRecord(ctx->gevent, st));
+    GSB_CUDA(cudaStreamWaitEvent(caller, ctx->gevent, 0));
+  }
   return GSB_OK;
 }
 

@@ -165,6 +165,61 @@ __global__ void __launch_bounds__(512) k_halo_copy(const HaloArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Coarse-level gather over NVLink peer memory: every rank stores its owned rows of the coarsest distributed
+// right-hand side straight into EVERY rank's copy of the full level (all-to-all posted writes, one flag per
+// source), replacing the NCCL all-gather of the V-cycle - the cycle then consists of this library's kernels only
+// and can be replayed from a CUDA graph on every rank.  Buffers are double-buffered by exchange parity; the
+// per-cycle residual all-reduce keeps ranks within one cycle of each other, so no consumed-acknowledgement is
+// needed.  The exchange number lives on the device (graph-replay safe), bumped by k_gather_wait.
+// ------------------------------------------------------------------------------------------
+constexpr int kGatherMaxWorld = 16;
+struct GatherPushArgs {
+  const double *rows;            // my owned rows (contiguous)
+  long long n, off, buf_doubles; // doubles to send, offset inside the level, doubles per buffer half
+  double *peer_buf[kGatherMaxWorld];
+  long long *peer_flags[kGatherMaxWorld];
+  int world, rank;
+  int *counters;                 // [world] CTA-arrival counters (zeroed once)
+  const long long *epoch;        // completed gathers
+};
+__global__ void __launch_bounds__(512) k_gather_push(const GatherPushArgs a) {
+  const int p = blockIdx.y;
+  const long long e = ld_sys(a.epoch) + 1;
+  double *dst = a.peer_buf[p] + (e & 1) * a.buf_doubles + a.off;
+  const long long per = (a.n + gridDim.x - 1) / gridDim.x;
+  const long long i0 = per * blockIdx.x, i1 = min(a.n, i0 + per);
+  for (long long i = i0 + threadIdx.x; i < i1; i += blockDim.x) dst[i] = a.rows[i];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int arrived = atomicAdd(a.counters + p, 1);
+    if (arrived == (int)gridDim.x - 1) {
+      a.counters[p] = 0;
+      __threadfence_system();
+      st_sys(a.peer_flags[p] + a.rank, e);
+    }
+  }
+}
+// wait for all `world` sources of this gather, copy the assembled level into `out`, bump the epoch
+__global__ void __launch_bounds__(512) k_gather_wait(const double *buf, long long buf_doubles, const long long *flags,
+                                                     int world, long long n_total, double *out, long long *epoch) {
+  __shared__ long long s_e;
+  if (threadIdx.x == 0) s_e = ld_sys(epoch) + 1;
+  __syncthreads();
+  const long long e = s_e;
+  if ((int)threadIdx.x < world)
+    while (ld_sys(flags + threadIdx.x) < e) __nanosleep(64);
+  __syncthreads();
+  const double *src = buf + (e & 1) * buf_doubles;
+  for (long long i = threadIdx.x; i < n_total; i += blockDim.x) out[i] = __ldcv(src + i);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    *epoch = e;
+  }
+}
+
 static int slab_plan(gsb_ctx *ctx) {
   // a slab context has exactly one level: the local array itself
   return ensure_plan(ctx, 1 << 30);
@@ -273,6 +328,35 @@ int gsb_halo_recv(double *halo_up, double *halo_dn, long long n, const double *i
   }
   const int nblk = (int)std::min<long long>(16, (n + 8191) / 8192);
   k_halo_copy<<<dim3(nblk, 2), 512, 0, (cudaStream_t)stream>>>(a);
+  GSB_LAUNCH_CHECK();
+  return GSB_OK;
+}
+
+int gsb_gather_push(const double *rows_dev, long long n, long long off, long long buf_doubles, void *const *peer_bufs,
+                    void *const *peer_flags, int world, int rank, int *counters, const long long *epoch, void *stream) {
+  GSB_REQUIRE(rows_dev && peer_bufs && peer_flags && counters && epoch, "gsb_gather_push: NULL argument");
+  GSB_REQUIRE(world >= 1 && world <= kGatherMaxWorld && rank >= 0 && rank < world, "gsb_gather_push: bad world / rank");
+  GSB_REQUIRE(n > 0 && off >= 0 && off + n <= buf_doubles, "gsb_gather_push: rows outside the level");
+  GatherPushArgs a{};
+  a.rows = rows_dev;
+  a.n = n, a.off = off, a.buf_doubles = buf_doubles;
+  for (int p = 0; p < world; ++p) {
+    GSB_REQUIRE(peer_bufs[p] && peer_flags[p], "gsb_gather_push: missing peer buffer");
+    a.peer_buf[p] = static_cast<double *>(peer_bufs[p]);
+    a.peer_flags[p] = static_cast<long long *>(peer_flags[p]);
+  }
+  a.world = world, a.rank = rank, a.counters = counters, a.epoch = epoch;
+  const int nblk = (int)std::min<long long>(8, (n + 4095) / 4096);
+  k_gather_push<<<dim3(nblk, world), 512, 0, (cudaStream_t)stream>>>(a);
+  GSB_LAUNCH_CHECK();
+  return GSB_OK;
+}
+
+int gsb_gather_wait(const double *buf_local, long long buf_doubles, const long long *flags_local, int world,
+                    long long n_total, double *out_dev, long long *epoch, void *stream) {
+  GSB_REQUIRE(buf_local && flags_local && out_dev && epoch, "gsb_gather_wait: NULL argument");
+  GSB_REQUIRE(world >= 1 && world <= kGatherMaxWorld && n_total > 0 && n_total <= buf_doubles, "gsb_gather_wait: bad sizes");
+  k_gather_wait<<<1, 512, 0, (cudaStream_t)stream>>>(buf_local, buf_doubles, flags_local, world, n_total, out_dev, epoch);
   GSB_LAUNCH_CHECK();
   return GSB_OK;
 }

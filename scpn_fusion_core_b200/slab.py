@@ -228,6 +228,7 @@ class SlabComm:
         self.bytes_sent = 0
         self.messages = 0
         self.peer = None
+        self.gather = None
         # bumped whenever the peer-memory transport is (re)created or torn down: a SlabMultigrid that cached raw
         # inbox / flag pointers (native descriptors, a captured graph) for an older generation must rebuild them
         self.peer_generation = 0
@@ -279,6 +280,92 @@ class SlabComm:
                      "epochs": torch.zeros(4, dtype=torch.int64, device=dev), "cap": max_doubles, "lib": lib}
         self.peer_generation += 1
         return True
+
+    def enable_peer_gather(self, device: int, level_doubles: int) -> bool:
+        """Gather the coarsest distributed right-hand side over NVLink peer memory (gsb_gather_push / gsb_gather_wait)
+        instead of an NCCL all-gather: every rank maps every rank's gather block through CUDA IPC.  Collective.
+        With it (and peer halos) a V-cycle consists of libgsb200 kernels only and is replayed from a CUDA graph on
+        every rank.  Returns False (NCCL keeps gathering) if IPC is unavailable or the group has more than 16 ranks."""
+        if getattr(self, "gather", None) is not None:
+            self.disable_peer_gather()
+        self.gather = None
+        if self.world == 1 or self.world > 16:
+            return False
+        import ctypes as C
+        torch, dist = self.torch, self.dist
+        lib = _lib.load()
+        dev = torch.device(f"cuda:{device}")
+        half = ((level_doubles * 8 + 255) // 256) * 256
+        total = 256 + 2 * half  # [world int64 flags, padded to 256 B | half 0 | half 1]
+        base = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        ok = 1 if lib.gsb_ipc_alloc(device, total, C.byref(base), handle) == 0 else 0
+        gathered: list = [None] * self.world
+        dist.all_gather_object(gathered, (ok, bytes(handle.raw)), group=self.group)
+        if not all(g[0] for g in gathered):
+            if ok:
+                lib.gsb_ipc_free(base)
+            return False
+        ptrs: list = [None] * self.world
+        opened = []
+        for r in range(self.world):
+            if r == self.rank:
+                ptrs[r] = base.value
+                continue
+            p = C.c_void_p()
+            if lib.gsb_ipc_open(device, gathered[r][1], C.byref(p)) != 0:
+                ok = 0
+                break
+            ptrs[r] = p.value
+            opened.append(p.value)
+        flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 0:
+            for q in opened:
+                lib.gsb_ipc_close(C.c_void_p(q))
+            dist.barrier(group=self.group)
+            lib.gsb_ipc_free(base)
+            return False
+        bufs = (C.c_void_p * self.world)(*[C.c_void_p(q + 256) for q in ptrs])
+        flags = (C.c_void_p * self.world)(*[C.c_void_p(q) for q in ptrs])
+        self.gather = {"base": base.value, "opened": opened, "bufs": bufs, "flags": flags, "half_doubles": half // 8,
+                       "cap": level_doubles, "counters": torch.zeros(self.world, dtype=torch.int32, device=dev),
+                       "epoch": torch.zeros(1, dtype=torch.int64, device=dev), "lib": lib}
+        self.peer_generation += 1
+        return True
+
+    def disable_peer_gather(self) -> None:
+        G = getattr(self, "gather", None)
+        if G is None:
+            return
+        import ctypes as C
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier(group=self.group)
+        for q in G["opened"]:
+            G["lib"].gsb_ipc_close(C.c_void_p(q))
+        G["lib"].gsb_ipc_free(C.c_void_p(G["base"]))
+        self.gather = None
+        self.peer_generation += 1
+
+    def gather_rows_peer(self, owned, rows_per_rank: int, nz: int, out) -> None:
+        """Peer-memory form of gather_rows: this rank's owned rows go straight into every rank's copy of the level;
+        `out` (nz, nr) receives the assembled level.  Stream-ordered, no host synchronisation."""
+        import ctypes as C
+        G = self.gather
+        nr = int(owned.shape[1])
+        n_rows = rows_per_rank + (1 if self.rank == self.world - 1 else 0)
+        if nz * nr > G["cap"]:
+            raise _lib.GsbError("peer gather buffer too small for this level")
+        st = C.c_void_p(self.torch.cuda.current_stream().cuda_stream)
+        vp = lambda t: C.c_void_p(t.data_ptr())
+        _lib.check(G["lib"].gsb_gather_push(vp(owned), n_rows * nr, self.rank * rows_per_rank * nr, G["half_doubles"], G["bufs"],
+                                            G["flags"], self.world, self.rank, vp(G["counters"]), vp(G["epoch"]), st),
+                   "gsb_gather_push")
+        _lib.check(G["lib"].gsb_gather_wait(G["bufs"][self.rank], G["half_doubles"], G["flags"][self.rank], self.world,
+                                            nz * nr, vp(out), vp(G["epoch"]), st), "gsb_gather_wait")
+        self.bytes_sent += (self.world - 1) * n_rows * nr * 8
+        self.messages += self.world - 1
 
     def disable_peer_halo(self) -> None:
         """Unmap the neighbours' IPC blocks and free this rank's (collective in spirit: call it on every rank
@@ -523,7 +610,8 @@ class SlabMultigrid:
             halo.flags_dn = dn["flags"] if dn else None
             halo.counters, halo.epochs, halo.cap = P["counters"].data_ptr(), P["epochs"].data_ptr(), P["cap"]
         self._native = {"descs": descs, "keep": keep, "d_last": d_last, "lo": lo, "hi": hi, "nzc": nzc,
-                        "roff_last": 2 * lo - self.levels[-1].row0, "halo": halo, "lib": lib}
+                        "roff_last": 2 * lo - self.levels[-1].row0, "halo": halo, "lib": lib,
+                        "d_full": ops.zeros((nzc, nrc)) if getattr(comm, "gather", None) is not None else None}
         return True
 
     def _vcycle_native(self) -> None:
@@ -534,9 +622,13 @@ class SlabMultigrid:
         st = D.stream_ptr()
         _lib.check(lib.gsb_slab_down(N["descs"], n, D.ptr(N["d_last"]), hp, self.halo, self.omega, self.pre, st),
                    "gsb_slab_down")
-        d_full = comm.gather_rows(N["d_last"], self.gathered["rows_per_rank"], N["nzc"])
+        if N["d_full"] is not None:  # NVLink peer-memory gather: own kernels only (graph replayable on every rank)
+            d_full = N["d_full"]
+            comm.gather_rows_peer(N["d_last"], self.gathered["rows_per_rank"], N["nzc"], d_full)
+        else:
+            d_full = comm.gather_rows(N["d_last"], self.gathered["rows_per_rank"], N["nzc"])
         e_full = ops.coarse_vcycle(self.gathered, d_full, self.omega, self.pre, self.post, self.min_grid)
-        e_loc = e_full[N["lo"]:N["hi"]].contiguous()
+        e_loc = e_full[N["lo"]:N["hi"]]  # whole rows of a contiguous array: no copy
         N["e_keep"] = e_loc
         _lib.check(lib.gsb_slab_up(N["descs"], n, D.ptr(e_loc), N["hi"] - N["lo"], N["roff_last"], hp, self.post + 1,
                                    self.omega, self.post, st), "gsb_slab_up")
@@ -600,7 +692,9 @@ class SlabMultigrid:
         # multi-rank graphs (NCCL gather + spin-wait halo kernels inside one captured graph) hung on the
         # 2/4-GPU box in round 1 and are therefore opt-in (GSB_SLAB_MULTI_RANK_GRAPH=1) until understood
         import os as _os
-        multi_ok = comm.world == 1 or _os.environ.get("GSB_SLAB_MULTI_RANK_GRAPH", "0") == "1"
+        # ... with the peer-memory gather the cycle holds no NCCL node any more and replays on every rank
+        all_own = bool(st["native"]) and getattr(comm, "gather", None) is not None and getattr(comm, "peer", None) is not None
+        multi_ok = comm.world == 1 or _os.environ.get("GSB_SLAB_MULTI_RANK_GRAPH", "1" if all_own else "0") == "1"
         want_graph = self.use_graph and multi_ok and getattr(x, "is_cuda", False) and graph is None
         while not residual < tol and cycles < max_cycles:
             if graph is not None:
