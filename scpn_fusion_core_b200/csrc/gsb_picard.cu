@@ -15,7 +15,7 @@
 
 #include <cstdlib>
 
-constexpr int kPT = 8;   // max partial blocks per equilibrium
+constexpr int kPT = 32;  // max partial blocks per equilibrium
 constexpr int kTW = 8;   // doubles per topo partial
 constexpr int kRW = 4;   // doubles per relax partial
 constexpr int kSadChunk = 4096;   // masked points per CTA of the saddle candidate kernel
@@ -103,17 +103,22 @@ k_topo(Bufs bufs, const int *__restrict__ cur, size_t n, int nz, int nr, GradGeo
   const int r0 = (int)((long long)nz * p / P), r1 = (int)((long long)nz * (p + 1) / P);
   ValIdx mx{0.0, -1}, mb{0.0, -1};
   double mn = INFINITY;
-  for (int idx = threadIdx.x; idx < (r1 - r0) * nr; idx += blockDim.x) {
-    const int iz = r0 + idx / nr, ir = idx % nr;
-    const int flat = iz * nr + ir;
-    const double v = f[flat];
-    mx = better<true>(mx, ValIdx{v, flat});
-    mn = fmin(mn, v);
-    if (rowmask[iz]) {
-      double gz, gr;
-      grad_point(f, nz, nr, iz, ir, gg, gz, gr);
-      const double bm = hypot_glibc(gr, gz);
-      if (isfinite(bm)) mb = better<false>(mb, ValIdx{bm, flat});
+  // rows of the block's band one at a time, threads across the columns: no integer division per point, the
+  // divertor-row test is uniform over the block, and a thread meets its points in increasing flat index
+#pragma unroll 4
+  for (int iz = r0; iz < r1; ++iz) {
+    const bool masked = rowmask[iz] != 0;
+    for (int ir = threadIdx.x; ir < nr; ir += blockDim.x) {
+      const int flat = iz * nr + ir;
+      const double v = f[flat];
+      if (mx.i < 0 || v > mx.v) mx = ValIdx{v, flat};  // strict >: the first maximum of this thread's sequence stays
+      mn = fmin(mn, v);
+      if (masked) {
+        double gz, gr;
+        grad_point(f, nz, nr, iz, ir, gg, gz, gr);
+        const double bm = hypot_glibc(gr, gz);
+        if (isfinite(bm) && (mb.i < 0 || bm < mb.v)) mb = ValIdx{bm, flat};
+      }
     }
   }
   mx = block_arg<true>(mx, shv, shi);
@@ -368,17 +373,60 @@ struct ProfileDev {
   double p[4], f[4];
 };
 
-__device__ __forceinline__ double mtanh_dev(double x, const double *q) {
-  // fusion_kernel.py:380-389 (caller guarantees 0 <= x < 1)
-  double y = __ddiv_rn(dsub(q[0], x), q[1]);
+// mtanh profile (fusion_kernel.py:380-389) with the two per-equilibrium divisors pre-inverted
+// (Markstein division, see gsb_internal.cuh)
+struct MtanhK {
+  double top, width, half_h, alpha, inv_top, inv_width;
+};
+__device__ __forceinline__ MtanhK mtanh_k(const double *q) {
+  MtanhK m;
+  m.top = q[0], m.width = q[1], m.half_h = dmul(0.5, q[2]), m.alpha = q[3];
+  m.inv_top = __ddiv_rn(1.0, q[0]);
+  m.inv_width = __ddiv_rn(1.0, q[1]);
+  return m;
+}
+// tanh(y) for |y| <= 20 as (1 - u)/(1 + u), u = exp(-2y): Cody-Waite reduction, degree-13 Taylor
+// polynomial on |r| <= ln2/2 (truncation 4e-18 relative), exponent add, then a Newton-refined
+// reciprocal.  Absolute error <= 4e-16 over the range (np.tanh itself is only accurate to ~1 ulp of
+// a result that is then added to 1.0), ~30 instructions instead of ~90 for the library tanh().
+__device__ __forceinline__ double tanh_lean(double y) {
+  const double x = -2.0 * y;  // exact
+  const int k = __double2int_rn(x * 1.4426950408889634074);
+  const double kf = (double)k;
+  double r = __fma_rn(-kf, 6.93147180369123816490e-01, x);
+  r = __fma_rn(-kf, 1.90821492927058770002e-10, r);
+  // Estrin evaluation of sum_{i<=13} r^i / i!: dependency depth 5 instead of 13 Horner steps (the
+  // evaluation is latency bound with 4 warps per scheduler)
+  const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
+  const double a0 = __fma_rn(r, 1.0, 1.0);
+  const double a1 = __fma_rn(r, 1.6666666666666666e-01, 0.5);
+  const double a2 = __fma_rn(r, 8.333333333333333e-03, 4.1666666666666664e-02);
+  const double a3 = __fma_rn(r, 1.984126984126984e-04, 1.388888888888889e-03);
+  const double a4 = __fma_rn(r, 2.7557319223985893e-06, 2.48015873015873e-05);
+  const double a5 = __fma_rn(r, 2.505210838544172e-08, 2.755731922398589e-07);
+  const double a6 = __fma_rn(r, 1.6059043836821613e-10, 2.08767569878681e-09);
+  const double b0 = __fma_rn(a1, r2, a0), b1 = __fma_rn(a3, r2, a2), b2 = __fma_rn(a5, r2, a4);
+  const double d0 = __fma_rn(b1, r4, b0), d1 = __fma_rn(a6, r4, b2);
+  const double p = __fma_rn(d1, r8, d0);
+  const double u = __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));  // |k| <= 58: no over/underflow
+  const double d = 1.0 + u, n = 1.0 - u;
+  double y0;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(d));
+  const double e = __fma_rn(-d, y0, 1.0);
+  y0 = __fma_rn(y0, e, y0);  // one Newton step (>= 40 bits); the residual correction below finishes the quotient
+  const double q = n * y0;
+  return __fma_rn(__fma_rn(-d, q, n), y0, q);
+}
+__device__ __forceinline__ double mtanh_res(double x, const MtanhK &m) {
+  double y = ddiv_yf(dsub(m.top, x), m.width, m.inv_width);
   y = fmin(fmax(y, -20.0), 20.0);
-  const double ped = dmul(dmul(0.5, q[2]), dadd(1.0, tanh(y)));
+  const double ped = dmul(m.half_h, dadd(1.0, tanh_lean(y)));
   double core = 0.0;
-  if (x < q[0]) {
-    const double t = __ddiv_rn(x, q[0]);
+  if (x < m.top) {
+    const double t = ddiv_yf(x, m.top, m.inv_top);
     core = fmax(0.0, dsub(1.0, dmul(t, t)));
   }
-  return dadd(ped, dmul(q[3], core));
+  return dadd(ped, dmul(m.alpha, core));
 }
 
 __global__ void __launch_bounds__(256)
@@ -400,28 +448,34 @@ k_source_raw(Bufs bufs, const int *__restrict__ cur, size_t n, int nz, int nr,
     pp[i] = prof_dev ? prof_dev[(size_t)b * 8 + i] : prof.p[i];
     pf[i] = prof_dev ? prof_dev[(size_t)b * 8 + 4 + i] : prof.f[i];
   }
+  // the same profile evaluation as the resident kernel (lean tanh, pre-inverted divisors, one evaluation when
+  // p' and FF' share their parameters): both Picard paths see identical profile values
+  const MtanhK mkp = mtanh_k(pp), mkf = mtanh_k(pf);
+  const bool same_prof = pp[0] == pf[0] && pp[1] == pf[1] && pp[2] == pf[2] && pp[3] == pf[3];
   const int r0 = (int)((long long)nz * p / P), r1 = (int)((long long)nz * (p + 1) / P);
   double acc = 0.0;
-  for (int idx = threadIdx.x; idx < (r1 - r0) * nr; idx += blockDim.x) {
-    const int iz = r0 + idx / nr, ir = idx % nr;
-    const size_t o = (size_t)iz * nr + ir;
-    const double pn = ddiv_y(dsub(f[o], psi_ax), denom, inv_denom);
-    const bool in = (pn >= 0.0) && (pn < 1.0);
-    double pr = 0.0, ff = 0.0;
-    if (in) {
-      if (prof.hmode) {
-        pr = mtanh_dev(pn, pp);
-        ff = mtanh_dev(pn, pf);
-      } else {
-        pr = dsub(1.0, pn);
-        ff = pr;
+  // rows of the block's band one at a time, threads across the columns (no integer division per point)
+#pragma unroll 2
+  for (int iz = r0; iz < r1; ++iz)
+    for (int ir = threadIdx.x; ir < nr; ir += blockDim.x) {
+      const size_t o = (size_t)iz * nr + ir;
+      const double pn = ddiv_yf(dsub(f[o], psi_ax), denom, inv_denom);
+      const bool in = (pn >= 0.0) && (pn < 1.0);
+      double pr = 0.0, ff = 0.0;
+      if (in) {
+        if (prof.hmode) {
+          pr = mtanh_res(pn, mkp);
+          ff = same_prof ? pr : mtanh_res(pn, mkf);
+        } else {
+          pr = dsub(1.0, pn);
+          ff = pr;
+        }
       }
+      // J_raw = 0.5*(R*p) + 0.5*((1/(mu0 R))*ff)      (fusion_kernel.py:430-434)
+      const double j = dadd(dmul(0.5, dmul(rrow[ir], pr)), dmul(0.5, dmul(cf[ir], ff)));
+      jraw[(size_t)b * n + o] = j;
+      acc += j;
     }
-    // J_raw = 0.5*(R*p) + 0.5*((1/(mu0 R))*ff)      (fusion_kernel.py:430-434)
-    const double j = dadd(dmul(0.5, dmul(rrow[ir], pr)), dmul(0.5, dmul(cf[ir], ff)));
-    jraw[(size_t)b * n + o] = j;
-    acc += j;
-  }
   acc = block_sum(acc, sh);
   if (threadIdx.x == 0) spart[(size_t)b * kPT + p] = acc;
 }
@@ -495,13 +549,28 @@ __device__ __forceinline__ double wall_or(const double *__restrict__ W, const do
   return W[(size_t)iz * nr + ir];
 }
 
-__global__ void __launch_bounds__(256)
+// Block = a chunk of up to 128 columns x a band of rows; a thread keeps its column and walks down the band with
+// a three-row register window of the RELAXED iterate, so a point costs three global loads (psi, Psi_new of the
+// row entering the window, the source) and one store; the east / west neighbours of the residual stencil come
+// from the adjacent lanes by warp shuffle (recomputed from memory only at the two edges of a warp).
+struct RelaxPlan {
+  int cc, n_cc, n_rb;  // columns per chunk, column chunks, row bands: P = n_cc * n_rb partial blocks
+};
+static RelaxPlan relax_plan(int nz, int nr) {
+  RelaxPlan r;
+  r.n_cc = (nr + 127) / 128;
+  r.cc = (((nr + r.n_cc - 1) / r.n_cc) + 31) / 32 * 32;
+  r.n_cc = (nr + r.cc - 1) / r.cc;
+  r.n_rb = std::max(1, std::min(12 / r.n_cc, nz / 16));  // <= 12 partial blocks: k_decide adds them serially
+  return r;
+}
+__global__ void __launch_bounds__(128)
 k_relax(LevelGeom g, Bufs bufs, const int *__restrict__ cur, const int *__restrict__ nxt,
         const double *__restrict__ Wall, const double *__restrict__ ringall,
         const double *__restrict__ srcall, double alpha, double oma, double *__restrict__ rpart,
-        const int *__restrict__ active) {
+        const int *__restrict__ active, RelaxPlan rp) {
   __shared__ double sh[32];
-  const int b = blockIdx.y, P = gridDim.x, p = blockIdx.x;
+  const int b = blockIdx.y, p = blockIdx.x;
   if (active && !active[b]) return;
   const int nz = g.nz, nr = g.nr;
   const size_t n = (size_t)nz * nr;
@@ -510,27 +579,73 @@ k_relax(LevelGeom g, Bufs bufs, const int *__restrict__ cur, const int *__restri
   const double *W = Wall + b * n;
   const double *ring = ringall + (size_t)b * ring_size(nz, nr);
   const double *src = srcall + b * n;
-  const int r0 = (int)((long long)nz * p / P), r1 = (int)((long long)nz * (p + 1) / P);
+  const int chunk = p % rp.n_cc, band = p / rp.n_cc;
+  const int ir = chunk * rp.cc + threadIdx.x;
+  const int z0 = (int)((long long)nz * band / rp.n_rb), z1 = (int)((long long)nz * (band + 1) / rp.n_rb);
+  const int lane = threadIdx.x & 31;
+  const bool col_on = ir < nr;
   double dsum = 0.0, rmax = 0.0, rsq = 0.0;
   int bad = 0;
-  for (int idx = threadIdx.x; idx < (r1 - r0) * nr; idx += blockDim.x) {
-    const int iz = r0 + idx / nr, ir = idx % nr;
-    const size_t o = (size_t)iz * nr + ir;
-    const double wn = wall_or(W, ring, nz, nr, iz, ir);
-    const double old = f[o];
-    if (isnan(wn) || isinf(wn)) bad = 1;
-    dsum += fabs(dsub(wn, old));
-    const double c = dadd(dmul(oma, old), dmul(alpha, wn));  // (1-a)*Psi + a*Psi_new
-    out[o] = c;
-    if (iz > 0 && ir > 0 && iz < nz - 1 && ir < nr - 1) {
-      const double e = dadd(dmul(oma, f[o + 1]), dmul(alpha, wall_or(W, ring, nz, nr, iz, ir + 1)));
-      const double w = dadd(dmul(oma, f[o - 1]), dmul(alpha, wall_or(W, ring, nz, nr, iz, ir - 1)));
-      const double s = dadd(dmul(oma, f[o - nr]), dmul(alpha, wall_or(W, ring, nz, nr, iz - 1, ir)));
-      const double nn = dadd(dmul(oma, f[o + nr]), dmul(alpha, wall_or(W, ring, nz, nr, iz + 1, ir)));
-      const double r = dsub(gs_apply(g, ir, c, e, w, s, nn), src[o]);
-      const double a = fabs(r);
-      if (a > rmax) rmax = a;
-      rsq += r * r;
+  // relaxed value at (iz, jc): (1-a)*Psi + a*Psi_new with the wall ring on the boundary (newton_solver.py:536)
+  auto relaxed = [&](int iz, int jc, double &wn, double &old) -> double {
+    wn = wall_or(W, ring, nz, nr, iz, jc);
+    old = f[(size_t)iz * nr + jc];
+    return dadd(dmul(oma, old), dmul(alpha, wn));
+  };
+  double wn, old;
+  double c_m = 0.0, c_0 = 0.0;
+  const bool int_col = col_on && ir > 0 && ir < nr - 1;
+  const double rs = int_col ? g.r_safe[ir] : 1.0, irs = int_col ? g.inv_r_safe[ir] : 1.0;
+  // (Psi_new, Psi) of the centre row travel with the window: every row is loaded exactly once per thread
+  double wn_0 = 0.0, old_0 = 0.0;
+  if (col_on) {
+    if (z0 > 0) c_m = relaxed(z0 - 1, ir, wn, old);
+    if (z0 < z1) c_0 = relaxed(z0, ir, wn_0, old_0);
+  }
+  constexpr int G = 4;  // rows per group: the loads of a whole group are in flight before the first use
+  for (int zb = z0; zb < z1; zb += G) {  // uniform trip count over the block (the shuffles need every lane)
+    double wnv[G], oldv[G], sv[G], ewn[G], eold[G];
+    // lanes 0 and 31 cannot get their west / east neighbour by shuffle: they fetch that column with the group
+    const int je = lane == 0 ? ir - 1 : ir + 1;
+    const bool edge = int_col && (lane == 0 || lane == 31);
+#pragma unroll
+    for (int u = 0; u < G; ++u) {
+      const int iz = zb + u;
+      const bool nx = col_on && iz < z1 && iz + 1 < nz;  // row iz+1 enters the window
+      const bool ctr = iz < z1 && iz > 0 && iz < nz - 1;
+      wnv[u] = nx ? wall_or(W, ring, nz, nr, iz + 1, ir) : 0.0;
+      oldv[u] = nx ? f[(size_t)(iz + 1) * nr + ir] : 0.0;
+      sv[u] = (int_col && ctr) ? src[(size_t)iz * nr + ir] : 0.0;
+      ewn[u] = (edge && ctr) ? wall_or(W, ring, nz, nr, iz, je) : 0.0;
+      eold[u] = (edge && ctr) ? f[(size_t)iz * nr + je] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < G; ++u) {
+      const int iz = zb + u;
+      if (iz < z1) {  // block-uniform
+        double c_p = 0.0;
+        if (col_on) {
+          // this row is the centre row now: its own statistics and its store happen here, exactly once per point
+          if (isnan(wn_0) || isinf(wn_0)) bad = 1;
+          dsum += fabs(dsub(wn_0, old_0));
+          out[(size_t)iz * nr + ir] = c_0;
+          if (iz + 1 < nz) c_p = dadd(dmul(oma, oldv[u]), dmul(alpha, wnv[u]));
+        }
+        double c_w = __shfl_up_sync(0xffffffffu, c_0, 1), c_e = __shfl_down_sync(0xffffffffu, c_0, 1);
+        if (int_col && iz > 0 && iz < nz - 1) {
+          const double c_edge = dadd(dmul(oma, eold[u]), dmul(alpha, ewn[u]));
+          if (lane == 0) c_w = c_edge;
+          if (lane == 31) c_e = c_edge;
+          const double r = dsub(gs_apply_v(g, rs, irs, c_0, c_e, c_w, c_m, c_p), sv[u]);
+          const double a = fabs(r);
+          if (a > rmax) rmax = a;
+          rsq += r * r;
+        }
+        c_m = c_0;
+        c_0 = c_p;
+        wn_0 = wnv[u];
+        old_0 = oldv[u];
+      }
     }
   }
   const int anybad = __syncthreads_or(bad);
@@ -771,62 +886,6 @@ __device__ __forceinline__ double grad_mag(const GradGeom &gg, double c, double 
   return hypot_glibc(gr, gz);
 }
 
-// mtanh profile (fusion_kernel.py:380-389) with the two per-equilibrium divisors pre-inverted
-// (Markstein division, see gsb_internal.cuh)
-struct MtanhK {
-  double top, width, half_h, alpha, inv_top, inv_width;
-};
-__device__ __forceinline__ MtanhK mtanh_k(const double *q) {
-  MtanhK m;
-  m.top = q[0], m.width = q[1], m.half_h = dmul(0.5, q[2]), m.alpha = q[3];
-  m.inv_top = __ddiv_rn(1.0, q[0]);
-  m.inv_width = __ddiv_rn(1.0, q[1]);
-  return m;
-}
-// tanh(y) for |y| <= 20 as (1 - u)/(1 + u), u = exp(-2y): Cody-Waite reduction, degree-13 Taylor
-// polynomial on |r| <= ln2/2 (truncation 4e-18 relative), exponent add, then a Newton-refined
-// reciprocal.  Absolute error <= 4e-16 over the range (np.tanh itself is only accurate to ~1 ulp of
-// a result that is then added to 1.0), ~30 instructions instead of ~90 for the library tanh().
-__device__ __forceinline__ double tanh_lean(double y) {
-  const double x = -2.0 * y;  // exact
-  const int k = __double2int_rn(x * 1.4426950408889634074);
-  const double kf = (double)k;
-  double r = __fma_rn(-kf, 6.93147180369123816490e-01, x);
-  r = __fma_rn(-kf, 1.90821492927058770002e-10, r);
-  // Estrin evaluation of sum_{i<=13} r^i / i!: dependency depth 5 instead of 13 Horner steps (the
-  // evaluation is latency bound with 4 warps per scheduler)
-  const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
-  const double a0 = __fma_rn(r, 1.0, 1.0);
-  const double a1 = __fma_rn(r, 1.6666666666666666e-01, 0.5);
-  const double a2 = __fma_rn(r, 8.333333333333333e-03, 4.1666666666666664e-02);
-  const double a3 = __fma_rn(r, 1.984126984126984e-04, 1.388888888888889e-03);
-  const double a4 = __fma_rn(r, 2.7557319223985893e-06, 2.48015873015873e-05);
-  const double a5 = __fma_rn(r, 2.505210838544172e-08, 2.755731922398589e-07);
-  const double a6 = __fma_rn(r, 1.6059043836821613e-10, 2.08767569878681e-09);
-  const double b0 = __fma_rn(a1, r2, a0), b1 = __fma_rn(a3, r2, a2), b2 = __fma_rn(a5, r2, a4);
-  const double d0 = __fma_rn(b1, r4, b0), d1 = __fma_rn(a6, r4, b2);
-  const double p = __fma_rn(d1, r8, d0);
-  const double u = __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));  // |k| <= 58: no over/underflow
-  const double d = 1.0 + u, n = 1.0 - u;
-  double y0;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(d));
-  const double e = __fma_rn(-d, y0, 1.0);
-  y0 = __fma_rn(y0, e, y0);  // one Newton step (>= 40 bits); the residual correction below finishes the quotient
-  const double q = n * y0;
-  return __fma_rn(__fma_rn(-d, q, n), y0, q);
-}
-__device__ __forceinline__ double mtanh_res(double x, const MtanhK &m) {
-  double y = ddiv_yf(dsub(m.top, x), m.width, m.inv_width);
-  y = fmin(fmax(y, -20.0), 20.0);
-  const double ped = dmul(m.half_h, dadd(1.0, tanh_lean(y)));
-  double core = 0.0;
-  if (x < m.top) {
-    const double t = ddiv_yf(x, m.top, m.inv_top);
-    core = fmax(0.0, dsub(1.0, dmul(t, t)));
-  }
-  return dadd(ped, dmul(m.alpha, core));
-}
-
 // block-wide broadcast of a value computed by thread 0 (through the scratch area)
 __device__ __forceinline__ double bcast_d(double v, int slot_off) {
   __syncthreads();
@@ -923,12 +982,12 @@ k_picard_resident(const __grid_constant__ RPlan plan, const __grid_constant__ Pi
           const int src_plane = c == 0 ? p0 : p1;
           const int oth_plane = c == 0 ? p1 : p0;
           const int dst_plane = c == 0 ? pt : p1;
-          for (int iz = warp; iz < nz; iz += nw) {
+          // slot walk (e = iz*hw + k over all 512 threads: every trip but the last is full; a warp-per-row loop
+          // leaves 31 of 32 lanes idle in the third trip of a 65-slot row)
+          for (int o = tid, iz = iz_first, k = k_first; o < nslot; o += T) {
             const int s = (c + iz) & 1;
-            for (int k = lane; k < hw; k += 32) {
-              const int ir = 2 * k + s;
-              if (ir >= nr) continue;
-              const int o = iz * hw + k;
+            const int ir = 2 * k + s;
+            if (ir < nr) {
               double v;
               if (iz == 0 || iz == nz - 1 || ir == 0 || ir == nr - 1) {
                 v = sanitize_fast(res_pool[src_plane + o]);
@@ -944,6 +1003,12 @@ k_picard_resident(const __grid_constant__ RPlan plan, const __grid_constant__ Pi
                 v = clip_cap(ddiv_y(acc, a_c0, inv_a_c0));
               }
               res_pool[dst_plane + o] = v;
+            }
+            k += step_k;
+            iz += step_z;
+            if (k >= hw) {
+              k -= hw;
+              ++iz;
             }
           }
           __syncthreads();
@@ -1603,7 +1668,7 @@ static int partials_for(int nz, int nr) {
   long long pts = (long long)nz * nr;
   int P = (int)((pts + 4095) / 4096);
   if (P < 1) P = 1;
-  if (P > kPT) P = kPT;
+  if (P > 8) P = 8;  // the per-equilibrium final kernels (k_topo_final, k_source_scale) walk the partials serially
   if (P > nz) P = nz;
   return P;
 }
@@ -1908,6 +1973,7 @@ static int picard_solve_impl(gsb_ctx *ctx, const gsb_picard_params *p, double *p
   }
 
   const double oma = 1.0 - p->alpha;
+  const RelaxPlan rplan = relax_plan(nz, nr);
   const int check_every = p->check_every > 0 ? p->check_every : 8;
   volatile double dr2 = ctx->dr * ctx->dr, dz2 = ctx->dz * ctx->dz, f1 = 4.0 * ctx->dr, f2 = f1 * ctx->dz;
   // one Picard iteration of every active equilibrium; `poll`: reset the active counter before the decision and
@@ -1945,10 +2011,11 @@ static int picard_solve_impl(gsb_ctx *ctx, const gsb_picard_params *p, double *p
       k_jacobi_from_cur<<<grd, blk, 0, st>>>(g, bufs, s.cur, w->source, w->W, s.active);
       GSB_LAUNCH_CHECK();
     }
-    k_relax<<<dim3(P, batch), 256, 0, st>>>(g, bufs, s.cur, s.nxt, w->W, w->ring, w->source, p->alpha, oma, w->rpart, s.active);
+    k_relax<<<dim3(rplan.n_cc * rplan.n_rb, batch), rplan.cc, 0, st>>>(g, bufs, s.cur, s.nxt, w->W, w->ring, w->source, p->alpha,
+                                                                      oma, w->rpart, s.active, rplan);
     GSB_LAUNCH_CHECK();
     if (poll) GSB_CUDA(cudaMemsetAsync(ctx->counter, 0, sizeof(int), st));
-    k_decide<<<(batch + 127) / 128, 128, 0, st>>>(s, w->rpart, P, (double)n, (double)(nz - 2) * (double)(nr - 2), p->tol,
+    k_decide<<<(batch + 127) / 128, 128, 0, st>>>(s, w->rpart, rplan.n_cc * rplan.n_rb, (double)n, (double)(nz - 2) * (double)(nr - 2), p->tol,
                                                   p->require_gs_residual, p->gs_tol, p->max_iterations, hist_dev,
                                                   gs_hist_dev, ctx->counter, batch);
     GSB_LAUNCH_CHECK();

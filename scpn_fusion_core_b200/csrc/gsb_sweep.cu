@@ -26,7 +26,7 @@ constexpr int kSwWPC = 4;    // warps per CTA (independent of each other)
 struct SweepArgs {
   int nz, nr;               // array shape (local rows incl. halo rows in slab mode)
   int par_off;              // added to the local row index for the colour parity (global row offset)
-  int band_rows, n_strips;  // tile plan
+  int band_rows, n_strips, n_bands;  // tile plan
   const double *in;
   double *out;
   const double *src;
@@ -167,11 +167,14 @@ __global__ void __launch_bounds__(32 * kSwWPC) k_sweep_warp(const SweepArgs a) {
   double *ring_s = ring_p + NRING * kSwCols;                   // [NRING][2][32]
   const int b = blockIdx.z;
   if (a.active && !a.active[b]) return;
-  const int strip = blockIdx.x * kSwWPC + wid;
-  if (strip >= a.n_strips) return;  // warps never synchronise with each other
+  // (strip, band) tiles are numbered linearly and dealt four to a CTA, so CTAs are full whatever the strip count
+  // (257 columns = 5 strips used to leave 3 of every 8 warp slots empty)
+  const int tile = blockIdx.x * kSwWPC + wid;
+  if (tile >= a.n_strips * a.n_bands) return;  // warps never synchronise with each other
+  const int band = tile / a.n_strips, strip = tile - band * a.n_strips;
   const int nz = a.nz, nr = a.nr;
   // tile: interior rows [z0,z1) x cols [c0,c1); loaded rows [zl,zh) x cols [cl,ch)
-  const int z0 = blockIdx.y * a.band_rows, z1 = min(nz, z0 + a.band_rows);
+  const int z0 = band * a.band_rows, z1 = min(nz, z0 + a.band_rows);
   const int c0 = strip * STEP, c1 = (a.n_strips == 1) ? nr : min(nr, c0 + STEP);  // one strip: nr <= 64
   const int zl = max(0, z0 - NST), zh = min(nz, z1 + NST);
   const int cl = max(0, c0 - NST), ch = min(nr, cl + kSwCols);  // cl is even (STEP and NST are)
@@ -209,7 +212,8 @@ void sweep_fused_plan(int nz, int nr, int batch, int nst, int num_sms, int *stri
   // a warp marches down its band row by row, ~1 us per row step when it is alone on its SM (measured on
   // 257^2..1025^2 single grids: 45 us per launch with 32-row bands, whatever the level): a level that cannot fill
   // the GPU is latency bound, so its bands shrink down to 8 rows - the 2*nst halo rows recomputed per band are
-  // free there, and the results do not depend on the tiling
+  // free there, and the results do not depend on the tiling.  (A cost model that also avoided band counts just
+  // past a wave boundary was measured and made things worse: full SMs are throughput bound, r2_streaming_picard.md.)
   if (warps < want) bands = (int)std::min<long long>((want + warps - 1) / warps, std::max(1, nz / 8));
   const int br = (nz + bands - 1) / bands;
   *band_rows = br;
@@ -231,6 +235,7 @@ int sweep_fused_launch(const LevelGeom &g, const double *in, size_t istride, dou
   int sc;
   sweep_fused_plan(g.nz, g.nr, batch, nst, num_sms, &sc, &a.band_rows, &ns, &nb);
   a.n_strips = ns;
+  a.n_bands = nb;
   GSB_REQUIRE(in != out || (ns == 1 && nb == 1), "sweep_fused_launch: in-place needs a single tile per equilibrium");
   a.in = in;
   a.out = out;
@@ -247,7 +252,7 @@ int sweep_fused_launch(const LevelGeom &g, const double *in, size_t istride, dou
   a.omw = 1.0 - omega;
   a.active = active;
   const size_t smem = sweep_smem_bytes(nst);
-  const dim3 grd((ns + kSwWPC - 1) / kSwWPC, nb, batch), blk(32 * kSwWPC, 1, 1);
+  const dim3 grd((ns * nb + kSwWPC - 1) / kSwWPC, 1, batch), blk(32 * kSwWPC, 1, 1);
   GSB_SMEM_OPT_IN(k_sweep_warp<2>, sweep_smem_bytes(2));
   GSB_SMEM_OPT_IN(k_sweep_warp<4>, sweep_smem_bytes(4));
   GSB_SMEM_OPT_IN(k_sweep_warp<6>, sweep_smem_bytes(6));

@@ -1,0 +1,6 @@
+#!/bin/bash
+O=gpurun_out
+python tools/bench_batch257.py 257 256
+python tools/bench_batch257.py 513 128
+python tools/bench_batch257.py 257 256 16 > $O/plain_b257.log 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $O/r2_b257_launches3.csv python tools/bench_batch257.py 257 256 16 > $O/ncu_b257.log 2>&1; tail -1 $O/ncu_b257.log
