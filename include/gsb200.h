@@ -307,11 +307,13 @@ int gsb_halo_recv(double *halo_up, double *halo_dn, long long n, const double *i
  * mapped here (own rank included).  gsb_gather_push stores `n` doubles (this rank's owned rows) at offset `off` of the
  * current half of every rank and raises flag[rank] there; gsb_gather_wait waits for all `world` flags, copies the
  * assembled n_total doubles into out_dev and bumps *epoch (device counter of completed gathers, zeroed once;
- * counters: `world` zeroed ints). */
+ * counters: `world` zeroed ints).  host_flag (NULL or mapped pinned host memory) receives the exchange number after
+ * out_dev is complete: with out_dev in pinned memory too, the host polls it instead of synchronising the stream
+ * (the per-cycle convergence norm of a slab solve travels this way: one value per rank, maximum taken on the host). */
 int gsb_gather_push(const double *rows_dev, long long n, long long off, long long buf_doubles, void *const *peer_bufs,
                     void *const *peer_flags, int world, int rank, int *counters, const long long *epoch, void *stream);
 int gsb_gather_wait(const double *buf_local, long long buf_doubles, const long long *flags_local, int world,
-                    long long n_total, double *out_dev, long long *epoch, void *stream);
+                    long long n_total, double *out_dev, long long *epoch, long long *host_flag, void *stream);
 
 /* Native driver of the distributed levels of one slab V-cycle: every launch of the descent
  * (gsb_slab_down) and of the ascent (gsb_slab_up) is issued from one call; the host gathers the

@@ -90,7 +90,7 @@ SIGNATURES = {
                               c_void_p, c_void_p]),
     "gsb_gather_push": (c_int, [c_void_p, c_longlong, c_longlong, c_longlong, POINTER(c_void_p), POINTER(c_void_p), c_int, c_int,
                                 c_void_p, c_void_p, c_void_p]),
-    "gsb_gather_wait": (c_int, [c_void_p, c_longlong, c_void_p, c_int, c_longlong, c_void_p, c_void_p, c_void_p]),
+    "gsb_gather_wait": (c_int, [c_void_p, c_longlong, c_void_p, c_int, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p]),
     "gsb_slab_down": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_double, c_int, c_void_p]),
     "gsb_slab_up": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_double, c_int, c_void_p]),
     "gsb_slab_single_tile": (c_int, [c_void_p, c_int]),

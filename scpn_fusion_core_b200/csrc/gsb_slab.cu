@@ -203,7 +203,8 @@ __global__ void __launch_bounds__(512) k_gather_push(const GatherPushArgs a) {
 }
 // wait for all `world` sources of this gather, copy the assembled level into `out`, bump the epoch
 __global__ void __launch_bounds__(512) k_gather_wait(const double *buf, long long buf_doubles, const long long *flags,
-                                                     int world, long long n_total, double *out, long long *epoch) {
+                                                     int world, long long n_total, double *out, long long *epoch,
+                                                     volatile long long *host_flag) {
   __shared__ long long s_e;
   if (threadIdx.x == 0) s_e = ld_sys(epoch) + 1;
   __syncthreads();
@@ -217,6 +218,7 @@ __global__ void __launch_bounds__(512) k_gather_wait(const double *buf, long lon
   if (threadIdx.x == 0) {
     __threadfence_system();
     *epoch = e;
+    if (host_flag) *host_flag = e;  // `out` (and this flag) may be mapped pinned host memory: the host polls, no stream sync
   }
 }
 
@@ -353,10 +355,11 @@ int gsb_gather_push(const double *rows_dev, long long n, long long off, long lon
 }
 
 int gsb_gather_wait(const double *buf_local, long long buf_doubles, const long long *flags_local, int world,
-                    long long n_total, double *out_dev, long long *epoch, void *stream) {
+                    long long n_total, double *out_dev, long long *epoch, long long *host_flag, void *stream) {
   GSB_REQUIRE(buf_local && flags_local && out_dev && epoch, "gsb_gather_wait: NULL argument");
   GSB_REQUIRE(world >= 1 && world <= kGatherMaxWorld && n_total > 0 && n_total <= buf_doubles, "gsb_gather_wait: bad sizes");
-  k_gather_wait<<<1, 512, 0, (cudaStream_t)stream>>>(buf_local, buf_doubles, flags_local, world, n_total, out_dev, epoch);
+  k_gather_wait<<<1, 512, 0, (cudaStream_t)stream>>>(buf_local, buf_doubles, flags_local, world, n_total, out_dev, epoch,
+                                                     host_flag);
   GSB_LAUNCH_CHECK();
   return GSB_OK;
 }

@@ -202,6 +202,14 @@ class CudaSlabOps:
                                                   D.stream_ptr()), "gsb_slab_residual_linf")
         return float(out.item())
 
+    def residual_linf_async(self, L: SlabLevel, x, f, row0: int, row1: int, out) -> None:
+        """Stream-ordered form: max |L x - f| of the local rows into the device scalar `out` (no host read)."""
+        D = self.D
+        ctx = self._context(L)
+        out.zero_()
+        _lib.check(ctx.lib.gsb_slab_residual_linf(ctx.handle, D.ptr(x), D.ptr(f), row0, row1, D.ptr(out),
+                                                  D.stream_ptr()), "gsb_slab_residual_linf")
+
     def coarse_vcycle(self, G: dict, d_full, omega: float, pre: int, post: int, min_grid: int):
         """The replicated tail of the V-cycle on the gathered level (zero initial guess): one gsb_vcycle
         call on a cached context of that level's geometry (multigrid_solve.py:252-335 from level `G`)."""
@@ -228,7 +236,7 @@ class SlabComm:
         self.bytes_sent = 0
         self.messages = 0
         self.peer = None
-        self.gather = None
+        self.gather = self.norm = None
         # bumped whenever the peer-memory transport is (re)created or torn down: a SlabMultigrid that cached raw
         # inbox / flag pointers (native descriptors, a captured graph) for an older generation must rebuild them
         self.peer_generation = 0
@@ -281,22 +289,15 @@ class SlabComm:
         self.peer_generation += 1
         return True
 
-    def enable_peer_gather(self, device: int, level_doubles: int) -> bool:
-        """Gather the coarsest distributed right-hand side over NVLink peer memory (gsb_gather_push / gsb_gather_wait)
-        instead of an NCCL all-gather: every rank maps every rank's gather block through CUDA IPC.  Collective.
-        With it (and peer halos) a V-cycle consists of libgsb200 kernels only and is replayed from a CUDA graph on
-        every rank.  Returns False (NCCL keeps gathering) if IPC is unavailable or the group has more than 16 ranks."""
-        if getattr(self, "gather", None) is not None:
-            self.disable_peer_gather()
-        self.gather = None
-        if self.world == 1 or self.world > 16:
-            return False
+    def _make_allgather(self, device: int, doubles: int):
+        """One all-to-all block {world int64 flags | two halves of `doubles`} per rank, mapped by every rank through
+        CUDA IPC (collective).  Returns None if IPC is unavailable on some rank."""
         import ctypes as C
         torch, dist = self.torch, self.dist
         lib = _lib.load()
         dev = torch.device(f"cuda:{device}")
-        half = ((level_doubles * 8 + 255) // 256) * 256
-        total = 256 + 2 * half  # [world int64 flags, padded to 256 B | half 0 | half 1]
+        half = ((doubles * 8 + 255) // 256) * 256
+        total = 256 + 2 * half
         base = C.c_void_p()
         handle = C.create_string_buffer(64)
         ok = 1 if lib.gsb_ipc_alloc(device, total, C.byref(base), handle) == 0 else 0
@@ -305,7 +306,7 @@ class SlabComm:
         if not all(g[0] for g in gathered):
             if ok:
                 lib.gsb_ipc_free(base)
-            return False
+            return None
         ptrs: list = [None] * self.world
         opened = []
         for r in range(self.world):
@@ -325,47 +326,97 @@ class SlabComm:
                 lib.gsb_ipc_close(C.c_void_p(q))
             dist.barrier(group=self.group)
             lib.gsb_ipc_free(base)
-            return False
+            return None
         bufs = (C.c_void_p * self.world)(*[C.c_void_p(q + 256) for q in ptrs])
         flags = (C.c_void_p * self.world)(*[C.c_void_p(q) for q in ptrs])
-        self.gather = {"base": base.value, "opened": opened, "bufs": bufs, "flags": flags, "half_doubles": half // 8,
-                       "cap": level_doubles, "counters": torch.zeros(self.world, dtype=torch.int32, device=dev),
-                       "epoch": torch.zeros(1, dtype=torch.int64, device=dev), "lib": lib}
+        return {"base": base.value, "opened": opened, "bufs": bufs, "flags": flags, "half_doubles": half // 8,
+                "cap": doubles, "counters": torch.zeros(self.world, dtype=torch.int32, device=dev),
+                "epoch": torch.zeros(1, dtype=torch.int64, device=dev), "lib": lib}
+
+    def _free_allgather(self, G) -> None:
+        import ctypes as C
+        for q in G["opened"]:
+            G["lib"].gsb_ipc_close(C.c_void_p(q))
+        G["lib"].gsb_ipc_free(C.c_void_p(G["base"]))
+
+    def enable_peer_gather(self, device: int, level_doubles: int) -> bool:
+        """Gather the coarsest distributed right-hand side AND the per-cycle convergence norm over NVLink peer memory
+        (gsb_gather_push / gsb_gather_wait) instead of NCCL collectives: every rank maps every rank's blocks through
+        CUDA IPC.  Collective.  With it (and peer halos) a V-cycle consists of libgsb200 kernels only and is replayed
+        from a CUDA graph on every rank; the norm lands in pinned host memory and the host polls it (no stream
+        synchronisation, no NCCL launch in the solve loop).  Returns False (NCCL keeps doing both) if IPC is
+        unavailable or the group has more than 16 ranks."""
+        if getattr(self, "gather", None) is not None:
+            self.disable_peer_gather()
+        self.gather = self.norm = None
+        if self.world == 1 or self.world > 16:
+            return False
+        g = self._make_allgather(device, level_doubles)
+        if g is None:
+            return False
+        m = self._make_allgather(device, self.world)
+        if m is None:
+            self._free_allgather(g)
+            return False
+        torch = self.torch
+        m["host"] = torch.zeros(self.world, dtype=torch.float64).pin_memory()      # one norm per rank
+        m["host_flag"] = torch.zeros(1, dtype=torch.int64).pin_memory()            # exchange number of `host`
+        m["local"] = torch.zeros(1, dtype=torch.float64, device=f"cuda:{device}")  # this rank's max |r| (bit pattern)
+        m["issued"] = 0
+        self.gather, self.norm = g, m
         self.peer_generation += 1
         return True
 
     def disable_peer_gather(self) -> None:
-        G = getattr(self, "gather", None)
-        if G is None:
+        if getattr(self, "gather", None) is None:
             return
-        import ctypes as C
         self.torch.cuda.synchronize()
         if self.world > 1:
             self.dist.barrier(group=self.group)
-        for q in G["opened"]:
-            G["lib"].gsb_ipc_close(C.c_void_p(q))
-        G["lib"].gsb_ipc_free(C.c_void_p(G["base"]))
-        self.gather = None
+        self._free_allgather(self.gather)
+        self._free_allgather(self.norm)
+        self.gather = self.norm = None
         self.peer_generation += 1
+
+    def _allgather_rows(self, G, owned, n: int, off: int, n_total: int, out, host_flag=None) -> None:
+        import ctypes as C
+        st = C.c_void_p(self.torch.cuda.current_stream().cuda_stream)
+        vp = lambda t: C.c_void_p(t.data_ptr())
+        _lib.check(G["lib"].gsb_gather_push(vp(owned), n, off, G["half_doubles"], G["bufs"], G["flags"], self.world, self.rank,
+                                            vp(G["counters"]), vp(G["epoch"]), st), "gsb_gather_push")
+        _lib.check(G["lib"].gsb_gather_wait(G["bufs"][self.rank], G["half_doubles"], G["flags"][self.rank], self.world, n_total,
+                                            vp(out), vp(G["epoch"]), None if host_flag is None else vp(host_flag), st),
+                   "gsb_gather_wait")
 
     def gather_rows_peer(self, owned, rows_per_rank: int, nz: int, out) -> None:
         """Peer-memory form of gather_rows: this rank's owned rows go straight into every rank's copy of the level;
         `out` (nz, nr) receives the assembled level.  Stream-ordered, no host synchronisation."""
-        import ctypes as C
         G = self.gather
         nr = int(owned.shape[1])
         n_rows = rows_per_rank + (1 if self.rank == self.world - 1 else 0)
         if nz * nr > G["cap"]:
             raise _lib.GsbError("peer gather buffer too small for this level")
-        st = C.c_void_p(self.torch.cuda.current_stream().cuda_stream)
-        vp = lambda t: C.c_void_p(t.data_ptr())
-        _lib.check(G["lib"].gsb_gather_push(vp(owned), n_rows * nr, self.rank * rows_per_rank * nr, G["half_doubles"], G["bufs"],
-                                            G["flags"], self.world, self.rank, vp(G["counters"]), vp(G["epoch"]), st),
-                   "gsb_gather_push")
-        _lib.check(G["lib"].gsb_gather_wait(G["bufs"][self.rank], G["half_doubles"], G["flags"][self.rank], self.world,
-                                            nz * nr, vp(out), vp(G["epoch"]), st), "gsb_gather_wait")
+        self._allgather_rows(G, owned, n_rows * nr, self.rank * rows_per_rank * nr, nz * nr, out)
         self.bytes_sent += (self.world - 1) * n_rows * nr * 8
         self.messages += self.world - 1
+
+    def norm_exchange_issue(self) -> None:
+        """Stream-ordered: publish this rank's max |r| (``self.norm["local"]``, filled by the residual kernel) to every
+        rank; the assembled per-rank values land in pinned host memory together with their exchange number."""
+        M = self.norm
+        self._allgather_rows(M, M["local"], 1, self.rank, self.world, M["host"], host_flag=M["host_flag"])
+
+    def norm_exchange_wait(self, expected: int) -> float:
+        """Host side: poll the pinned exchange number (no stream synchronisation), then max over the ranks (NaN wins)."""
+        M = self.norm
+        flag, host = M["host_flag"], M["host"]
+        import time as _t
+        t0 = _t.perf_counter()
+        while int(flag[0]) < expected:
+            if _t.perf_counter() - t0 > 120.0:
+                raise _lib.GsbError("slab norm exchange timed out (a peer rank stopped issuing exchanges)")
+        vals = host.numpy().copy()
+        return float("nan") if np.isnan(vals).any() else float(vals.max())
 
     def disable_peer_halo(self) -> None:
         """Unmap the neighbours' IPC blocks and free this rank's (collective in spirit: call it on every rank
@@ -668,7 +719,23 @@ class SlabMultigrid:
         x.copy_(bc)
         r0, r1 = max(1, L.g0) - L.row0, min(L.nz - 1, L.g1) - L.row0
         comm.exchange(x, L, self.halo)  # serves the residual (1 row) and the next V-cycle (all rows)
-        residual = comm.max(ops.residual_linf(L, x, f, r0, r1))
+        # convergence norm: with the peer-memory transports every rank publishes its max |r| to all ranks from the
+        # stream and the host polls pinned memory (no NCCL launch, no stream synchronisation in the loop)
+        use_norm = bool(st["native"]) and getattr(comm, "norm", None) is not None and getattr(x, "is_cuda", False)
+
+        def norm_issue():
+            ops.residual_linf_async(L, x, f, r0, r1, comm.norm["local"])
+            comm.norm_exchange_issue()
+
+        def norm_wait():
+            comm.norm["issued"] += 1
+            return comm.norm_exchange_wait(comm.norm["issued"])
+
+        if use_norm:
+            norm_issue()
+            residual = norm_wait()
+        else:
+            residual = comm.max(ops.residual_linf(L, x, f, r0, r1))
         cycles = 0
         def cycle(xc):
             if st["native"]:
@@ -683,6 +750,8 @@ class SlabMultigrid:
             if L.g1 == L.nz:
                 xc[L.h_top + n_own - 1] = bc[L.h_top + n_own - 1]
             comm.exchange(xc, L, self.halo)
+            if use_norm and xc.data_ptr() == x.data_ptr():
+                norm_issue()  # part of the (captured) cycle: residual of the new iterate + its exchange
             return xc
 
         # CUDA graph: the first cycle runs eagerly (it also creates every context and buffer); from the
@@ -697,12 +766,14 @@ class SlabMultigrid:
         multi_ok = comm.world == 1 or _os.environ.get("GSB_SLAB_MULTI_RANK_GRAPH", "1" if all_own else "0") == "1"
         want_graph = self.use_graph and multi_ok and getattr(x, "is_cuda", False) and graph is None
         while not residual < tol and cycles < max_cycles:
+            issued_in_cycle = True
             if graph is not None:
                 graph.replay()
             else:
                 x2 = cycle(x)
                 if x2.data_ptr() != x.data_ptr() if hasattr(x2, "data_ptr") else x2 is not x:
                     x.copy_(x2)  # multi-launch smoothing phases may end in a pooled buffer
+                    issued_in_cycle = False
                 if want_graph and cycles == 0:
                     import torch
                     torch.cuda.synchronize()
@@ -724,7 +795,12 @@ class SlabMultigrid:
                             graph = None
                     st["graph"] = graph
                     want_graph = graph is not None
-            residual = comm.max(ops.residual_linf(L, x, f, r0, r1))
+            if use_norm:
+                if not issued_in_cycle:
+                    norm_issue()
+                residual = norm_wait()
+            else:
+                residual = comm.max(ops.residual_linf(L, x, f, r0, r1))
             cycles += 1
         self.used_graph = graph is not None
         return x[own].clone(), residual, cycles, bool(residual < tol)
