@@ -983,32 +983,44 @@ k_picard_resident(const __grid_constant__ RPlan plan, const __grid_constant__ Pi
           const int oth_plane = c == 0 ? p1 : p0;
           const int dst_plane = c == 0 ? pt : p1;
           // slot walk (e = iz*hw + k over all 512 threads: every trip but the last is full; a warp-per-row loop
-          // leaves 31 of 32 lanes idle in the third trip of a 65-slot row)
-          for (int o = tid, iz = iz_first, k = k_first; o < nslot; o += T) {
-            const int s = (c + iz) & 1;
-            const int ir = 2 * k + s;
-            if (ir < nr) {
-              double v;
-              if (iz == 0 || iz == nz - 1 || ir == 0 || ir == nr - 1) {
-                v = sanitize_fast(res_pool[src_plane + o]);
-              } else {
-                const double cc = sanitize_fast(res_pool[oth_plane + o]);
-                const double side = sanitize_fast(res_pool[oth_plane + o - 1 + 2 * s]);
-                const double S = sanitize_fast(res_pool[oth_plane + o - hw]), N = sanitize_fast(res_pool[oth_plane + o + hw]);
-                const double f = sanitize_fast(__ldcg(wsrc + c * ps + o));
-                double acc = dadd(dmul(__ldg(tab_ae + ir), s ? side : cc), dmul(__ldg(tab_ae + nr + ir), s ? cc : side));
-                acc = dadd(acc, dmul(a_ns0, S));
-                acc = dadd(acc, dmul(a_ns0, N));
-                acc = dsub(acc, f);
-                v = clip_cap(ddiv_y(acc, a_c0, inv_a_c0));
-              }
-              res_pool[dst_plane + o] = v;
+          // leaves 31 of 32 lanes idle in the third trip of a 65-slot row), four slots per batch so that the four
+          // right-hand-side loads (L2) are in flight before the first use
+          int o = tid, iz = iz_first, k = k_first;
+          while (o < nslot) {
+            int vo[4], vz[4], vk[4];
+            double vf[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              vo[u] = o, vz[u] = iz, vk[u] = k;
+              const int s = (c + iz) & 1;
+              const int ir = 2 * k + s;
+              const bool interior = o < nslot && ir < nr && iz > 0 && iz < nz - 1 && ir > 0 && ir < nr - 1;
+              vf[u] = interior ? __ldcg(wsrc + c * ps + o) : 0.0;
+              o += T, k += step_k, iz += step_z;
+              if (k >= hw) k -= hw, ++iz;
             }
-            k += step_k;
-            iz += step_z;
-            if (k >= hw) {
-              k -= hw;
-              ++iz;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int oo = vo[u], zz = vz[u];
+              const int s = (c + zz) & 1;
+              const int ir = 2 * vk[u] + s;
+              if (oo < nslot && ir < nr) {
+                double v;
+                if (zz == 0 || zz == nz - 1 || ir == 0 || ir == nr - 1) {
+                  v = sanitize_fast(res_pool[src_plane + oo]);
+                } else {
+                  const double cc = sanitize_fast(res_pool[oth_plane + oo]);
+                  const double side = sanitize_fast(res_pool[oth_plane + oo - 1 + 2 * s]);
+                  const double S = sanitize_fast(res_pool[oth_plane + oo - hw]), N = sanitize_fast(res_pool[oth_plane + oo + hw]);
+                  const double f = sanitize_fast(vf[u]);
+                  double acc = dadd(dmul(__ldg(tab_ae + ir), s ? side : cc), dmul(__ldg(tab_ae + nr + ir), s ? cc : side));
+                  acc = dadd(acc, dmul(a_ns0, S));
+                  acc = dadd(acc, dmul(a_ns0, N));
+                  acc = dsub(acc, f);
+                  v = clip_cap(ddiv_y(acc, a_c0, inv_a_c0));
+                }
+                res_pool[dst_plane + oo] = v;
+              }
             }
           }
           __syncthreads();

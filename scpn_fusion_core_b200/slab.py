@@ -765,8 +765,12 @@ class SlabMultigrid:
         all_own = bool(st["native"]) and getattr(comm, "gather", None) is not None and getattr(comm, "peer", None) is not None
         multi_ok = comm.world == 1 or _os.environ.get("GSB_SLAB_MULTI_RANK_GRAPH", "1" if all_own else "0") == "1"
         want_graph = self.use_graph and multi_ok and getattr(x, "is_cuda", False) and graph is None
+        import time as _time
+        trace = _os.environ.get("GSB_SLAB_TRACE") == "1"
+        t_launch = t_wait = 0.0
         while not residual < tol and cycles < max_cycles:
             issued_in_cycle = True
+            _t0 = _time.perf_counter()
             if graph is not None:
                 graph.replay()
             else:
@@ -795,12 +799,18 @@ class SlabMultigrid:
                             graph = None
                     st["graph"] = graph
                     want_graph = graph is not None
+            _t1 = _time.perf_counter()
             if use_norm:
                 if not issued_in_cycle:
                     norm_issue()
                 residual = norm_wait()
             else:
                 residual = comm.max(ops.residual_linf(L, x, f, r0, r1))
+            t_launch += _t1 - _t0
+            t_wait += _time.perf_counter() - _t1
             cycles += 1
+        if trace and comm.rank == 0:
+            print(f"[slab trace] cycles {cycles}: host time issuing cycles {t_launch * 1e3:.2f} ms, waiting for the norm "
+                  f"{t_wait * 1e3:.2f} ms (graph={graph is not None}, polled norm={use_norm})", flush=True)
         self.used_graph = graph is not None
         return x[own].clone(), residual, cycles, bool(residual < tol)
