@@ -96,6 +96,18 @@ def workload_text(workload: str, grid: int, batch: int, scaling: str) -> str:
             "pedestal params +-3-10 %")
 
 
+def static_config(args, batch_per_gpu: int, total: int) -> dict:
+    """The workload description: identical in the B200 arm and in the reference arm (run-dependent numbers live in
+    `stats`, the reference arm's bounded sample in `cpu_baseline.sample`)."""
+    n_pts = args.grid ** 2
+    return {"workload": workload_text(args.workload, args.grid, args.batch, args.scaling),
+            "grid": [args.grid, args.grid], "batch_per_gpu": batch_per_gpu, "global_batch": total,
+            "method": "picard+multigrid(3,3,omega=1.6)", "tol": 1e-4,
+            "l2_policy": f"working set {3 * batch_per_gpu * n_pts * 8 / 2 ** 20:.0f} MiB of fields per step exceeds the "
+                         "126 MB L2" if batch_per_gpu * n_pts * 8 > 126e6 else
+                         "working set fits L2 (small --batch run; not the headline configuration)"}
+
+
 # ------------------------------------------------------------------------------------ CPU arm
 def _cpu_one(args):
     cfg, cc, ip, ped, workload, keep = args
@@ -121,49 +133,67 @@ def _cpu_one(args):
     return out
 
 
-def cpu_sweep(n_samples: int, cores: int, seed0: int, workload: str, grid: int = GRID, keep: int = 0):
+def cpu_sweep(n_samples: int, cores: int, seed0: int, workload: str, grid: int = GRID, keep: int = 0, pool=None):
     """Time `n_samples` oracle solves on a `cores`-process pool; returns (eq/s, seconds, per-sample results)."""
     import multiprocessing as mp
     cc, ip, ped = uq_inputs(n_samples, seed0)
     jobs = [(base_config(grid), cc[k], ip[k], ped[k], workload, k < keep) for k in range(n_samples)]
     os.environ.setdefault("OMP_NUM_THREADS", "1")
-    ctx = mp.get_context("fork")
-    with ctx.Pool(cores) as pool:
+    own = pool is None
+    if own:
+        pool = mp.get_context("fork").Pool(cores)
         pool.map(_cpu_one, [j[:5] + (False,) for j in jobs[:cores]])  # warm the workers (imports, page-in)
+    try:
         t0 = time.perf_counter()
         out = pool.map(_cpu_one, jobs)
         dt = time.perf_counter() - t0
+    finally:
+        if own:
+            pool.close()
+            pool.join()
     return n_samples / dt, dt, out
 
 
 def run_reference_arm(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
     if args.workload == "slab":
         print(json.dumps({"impl": "reference", "unavailable": "the slab workload has no CPU arm in bench.py "
                           "(tests/golden/make_golden.py mg_4097 times the reference's multigrid_solve: minutes per solve)"}))
         return
+    import multiprocessing as mp
     cores = os.cpu_count() or 1
-    n = 2 * max(cores, 2) if args.workload == "free_boundary" else 4 * max(cores, 2)
+    n = max(cores, 2)  # one sample per core and step: K steps stay within a few minutes (3.6 s per free-boundary sample)
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    pool = mp.get_context("fork").Pool(cores)
     times, rates = [], []
-    for s in range(args.steps):
-        rate, dt, _ = cpu_sweep(n, cores, 2026 + 1000 * s, args.workload, args.grid)
-        times.append(dt)
-        rates.append(rate)
+    try:
+        for s in range(max(args.warmup, 1)):  # warm-up steps: imports, page-in, first-touch of every worker
+            cpu_sweep(min(n, cores), cores, 2026, args.workload, args.grid, pool=pool)
+        for s in range(args.steps):
+            rate, dt, _ = cpu_sweep(n, cores, 2026 + 1000 * s, args.workload, args.grid, pool=pool)
+            times.append(dt)
+            rates.append(rate)
+    finally:
+        pool.close()
+        pool.join()
     value = float(np.mean(rates))
+    if args.scaling == "strong":
+        total, per_gpu = args.batch, -(-args.batch // max(world, 1))
+    else:
+        total, per_gpu = world * args.batch, args.batch
     line = {
         "impl": "reference", "metric": "converged_equilibria_per_s", "value": value, "unit": "equilibria/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * float(np.mean(times)), "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_text(args.workload, args.grid, args.batch, args.scaling),
-                   "grid": [args.grid, args.grid], "batch": args.batch, "method": "picard+multigrid(3,3,omega=1.6)",
-                   "tol": 1e-4, "sample": f"each step solves a bounded sample of {n} of the equilibria on the host cores"},
+        "config": static_config(args, per_gpu, total),
         "cpu_baseline": {"value": value, "unit": "equilibria/s", "cores": cores, "kind": "port",
-                         "sample": f"{n} equilibria per step on a {cores}-process pool (NumPy port of the reference's "
-                                   "solve_free_boundary / solve_equilibrium; the reference is Python and cannot travel to "
-                                   "the GPU box)"},
+                         "sample": f"each step solves a bounded sample of {n} of the equilibria on a {cores}-process pool "
+                                   "(NumPy port of the reference's solve_free_boundary / solve_equilibrium; the reference "
+                                   "is Python and cannot travel to the GPU box)"},
         "e2e": {"value": value, "unit": "equilibria/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -511,15 +541,10 @@ def run_gpu_arm(args) -> None:
             "metric": "converged_equilibria_per_s", "value": value, "unit": "equilibria/s", "n_gpus": world,
             "steps": args.steps, "warmup": warm, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_text(args.workload, args.grid, args.batch, args.scaling),
-                       "grid": [args.grid, args.grid], "batch_per_gpu": B, "global_batch": total,
-                       "method": "picard+multigrid(3,3,omega=1.6)", "tol": 1e-4,
-                       "l2_policy": f"working set {3 * B * n_pts * 8 / 2 ** 20:.0f} MiB of fields per step exceeds the 126 MB "
-                                    "L2" if B * n_pts * 8 > 126e6 else
-                                    "working set fits L2 (small --batch run; not the headline configuration)",
-                       "converged": n_conv, "unconverged": total - n_conv,
-                       "picard_iterations_mean": float(iters.mean()), "picard_iterations_max": int(iters.max()),
-                       "outer_iterations_max": int(outer.max())},
+            "config": static_config(args, B, total),
+            "stats": {"converged": n_conv, "unconverged": total - n_conv,
+                      "picard_iterations_mean": float(iters.mean()), "picard_iterations_max": int(iters.max()),
+                      "outer_iterations_max": int(outer.max())},
             "e2e": {"value": e2e, "unit": "equilibria/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": ("BatchedFusionKernel.solve_free_boundary" if free_boundary else "BatchedFusionKernel.solve") +
