@@ -586,38 +586,58 @@ k_relax(LevelGeom g, Bufs bufs, const int *__restrict__ cur, const int *__restri
   const bool col_on = ir < nr;
   double dsum = 0.0, rmax = 0.0, rsq = 0.0;
   int bad = 0;
-  // relaxed value at (iz, jc): (1-a)*Psi + a*Psi_new with the wall ring on the boundary (newton_solver.py:536)
-  auto relaxed = [&](int iz, int jc, double &wn, double &old) -> double {
-    wn = wall_or(W, ring, nz, nr, iz, jc);
-    old = f[(size_t)iz * nr + jc];
-    return dadd(dmul(oma, old), dmul(alpha, wn));
+  // Per-thread constants hoisted out of the row loop (the kernel was instruction bound: ~240 instructions per point
+  // with index-generic wall handling): column pointers, and where this column's Psi_new comes from - the wall ring
+  // for the two wall columns (indexed by row), the ring rows for the two wall rows, the V-cycle output otherwise.
+  const int jc = col_on ? ir : nr - 1;
+  const bool wcol = jc == 0 || jc == nr - 1;
+  const double *fcol = f + jc, *wcolp = W + jc, *scol = src + jc;
+  double *ocol = out + jc;
+  const double *ring_c = ring + 2 * nr + (jc ? nz : 0);  // wall column values, [iz]
+  // Psi_new at (iz, this column); `off` = iz * nr
+  auto psi_new = [&](int iz, size_t off) -> double {
+    if (wcol) return ring_c[iz];
+    if (iz == 0) return ring[jc];
+    if (iz == nz - 1) return ring[nr + jc];
+    return wcolp[off];
   };
-  double wn, old;
-  double c_m = 0.0, c_0 = 0.0;
+  // lanes 0 and 31 cannot get their west / east neighbour by shuffle: they fetch that column themselves
   const bool int_col = col_on && ir > 0 && ir < nr - 1;
+  const bool edge = int_col && (lane == 0 || lane == 31);
+  const int je = lane == 0 ? jc - 1 : min(jc + 1, nr - 1);
+  const bool wcol_e = je == 0 || je == nr - 1;
+  const double *ring_e = ring + 2 * nr + (je ? nz : 0);
   const double rs = int_col ? g.r_safe[ir] : 1.0, irs = int_col ? g.inv_r_safe[ir] : 1.0;
-  // (Psi_new, Psi) of the centre row travel with the window: every row is loaded exactly once per thread
-  double wn_0 = 0.0, old_0 = 0.0;
+  // three-row window of the relaxed iterate (1-a)*Psi + a*Psi_new (newton_solver.py:536) at this column; (Psi_new, Psi)
+  // of the centre row travel with it, so every row is loaded exactly once per thread
+  double c_m = 0.0, c_0 = 0.0, wn_0 = 0.0, old_0 = 0.0;
   if (col_on) {
-    if (z0 > 0) c_m = relaxed(z0 - 1, ir, wn, old);
-    if (z0 < z1) c_0 = relaxed(z0, ir, wn_0, old_0);
+    if (z0 > 0) {
+      const size_t o = (size_t)(z0 - 1) * nr;
+      c_m = dadd(dmul(oma, fcol[o]), dmul(alpha, psi_new(z0 - 1, o)));
+    }
+    if (z0 < z1) {
+      const size_t o = (size_t)z0 * nr;
+      wn_0 = psi_new(z0, o);
+      old_0 = fcol[o];
+      c_0 = dadd(dmul(oma, old_0), dmul(alpha, wn_0));
+    }
   }
   constexpr int G = 4;  // rows per group: the loads of a whole group are in flight before the first use
-  for (int zb = z0; zb < z1; zb += G) {  // uniform trip count over the block (the shuffles need every lane)
+  size_t off = (size_t)z0 * nr;  // row offset of the group's first row
+  for (int zb = z0; zb < z1; zb += G, off += (size_t)G * nr) {  // uniform trip count over the block (shuffles)
     double wnv[G], oldv[G], sv[G], ewn[G], eold[G];
-    // lanes 0 and 31 cannot get their west / east neighbour by shuffle: they fetch that column with the group
-    const int je = lane == 0 ? ir - 1 : ir + 1;
-    const bool edge = int_col && (lane == 0 || lane == 31);
 #pragma unroll
     for (int u = 0; u < G; ++u) {
       const int iz = zb + u;
+      const size_t o = off + (size_t)u * nr;
       const bool nx = col_on && iz < z1 && iz + 1 < nz;  // row iz+1 enters the window
       const bool ctr = iz < z1 && iz > 0 && iz < nz - 1;
-      wnv[u] = nx ? wall_or(W, ring, nz, nr, iz + 1, ir) : 0.0;
-      oldv[u] = nx ? f[(size_t)(iz + 1) * nr + ir] : 0.0;
-      sv[u] = (int_col && ctr) ? src[(size_t)iz * nr + ir] : 0.0;
-      ewn[u] = (edge && ctr) ? wall_or(W, ring, nz, nr, iz, je) : 0.0;
-      eold[u] = (edge && ctr) ? f[(size_t)iz * nr + je] : 0.0;
+      wnv[u] = nx ? psi_new(iz + 1, o + nr) : 0.0;
+      oldv[u] = nx ? fcol[o + nr] : 0.0;
+      sv[u] = (int_col && ctr) ? scol[o] : 0.0;
+      ewn[u] = (edge && ctr) ? (wcol_e ? ring_e[iz] : W[o + je]) : 0.0;
+      eold[u] = (edge && ctr) ? f[o + je] : 0.0;
     }
 #pragma unroll
     for (int u = 0; u < G; ++u) {
@@ -626,19 +646,22 @@ k_relax(LevelGeom g, Bufs bufs, const int *__restrict__ cur, const int *__restri
         double c_p = 0.0;
         if (col_on) {
           // this row is the centre row now: its own statistics and its store happen here, exactly once per point
-          if (isnan(wn_0) || isinf(wn_0)) bad = 1;
+          if (!(fabs(wn_0) <= 1.79769313486231570815e308)) bad = 1;  // NaN or +-inf
           dsum += fabs(dsub(wn_0, old_0));
-          out[(size_t)iz * nr + ir] = c_0;
+          ocol[off + (size_t)u * nr] = c_0;
           if (iz + 1 < nz) c_p = dadd(dmul(oma, oldv[u]), dmul(alpha, wnv[u]));
         }
         double c_w = __shfl_up_sync(0xffffffffu, c_0, 1), c_e = __shfl_down_sync(0xffffffffu, c_0, 1);
         if (int_col && iz > 0 && iz < nz - 1) {
-          const double c_edge = dadd(dmul(oma, eold[u]), dmul(alpha, ewn[u]));
-          if (lane == 0) c_w = c_edge;
-          if (lane == 31) c_e = c_edge;
+          if (edge) {
+            const double c_edge = dadd(dmul(oma, eold[u]), dmul(alpha, ewn[u]));
+            if (lane == 0)
+              c_w = c_edge;
+            else
+              c_e = c_edge;
+          }
           const double r = dsub(gs_apply_v(g, rs, irs, c_0, c_e, c_w, c_m, c_p), sv[u]);
-          const double a = fabs(r);
-          if (a > rmax) rmax = a;
+          rmax = fmax(rmax, fabs(r));
           rsq += r * r;
         }
         c_m = c_0;
