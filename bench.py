@@ -47,10 +47,11 @@ GRID = 129
 COIL_SCALE = 1.0e6  # config currents are MA; the reference's SI-mu0 coil flux wants amperes (tests/golden/make_golden.py)
 # Measured constants of the dominant kernel from this round's committed ncu --set full capture (profiles/);
 # None until a capture of the current kernel exists.
-# r2 capture (profiles/r2_picard_resident.md): ncu --set full of ONE k_picard_resident launch = one 4096-sample
-# fixed-boundary sweep, 367 540 Picard iterations: DRAM 20.29 GB read + 115.53 GB written, FP64 pipe 26.13 % active.
-TRAFFIC_NCU_PER_ITER = 135.82e9 / 367540.0   # DRAM bytes per Picard iteration (workspace write-back dominates)
-DP_WARP_INSTR_PER_ITER = 150.2e3             # FP64 warp instructions per Picard iteration (pipe-active cycles x 4 / 2)
+# r2 captures (profiles/r2_picard_resident.md) of ONE k_picard_resident launch = one 4096-sample fixed-boundary sweep,
+# 367 540 Picard iterations, final code of the round: DRAM 2.55 GB read + 38.42 GB written (135.8 GB before the J plane
+# was dropped from the per-CTA workspace), FP64 pipe 26.3 % active.
+TRAFFIC_NCU_PER_ITER = 40.97e9 / 367540.0    # DRAM bytes per Picard iteration (workspace write-back dominates)
+DP_WARP_INSTR_PER_ITER = 151.3e3             # FP64 warp instructions per Picard iteration (pipe-active cycles x 4 / 2)
 NCU_SOURCE = "profiles/r2_picard_resident.md"
 ITER_COILS = [(3.5, 3.0, -1.0), (8.0, 3.0, 4.0), (9.5, 0.0, 6.0), (8.0, -3.0, 4.0), (3.5, -3.0, -1.0),
               (9.5, 3.0, 3.0), (2.1, 0.0, 0.0)]

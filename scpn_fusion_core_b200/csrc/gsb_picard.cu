@@ -850,8 +850,7 @@ struct PicardResArgs {
   double *summary;          // [B][16] out
   double *hist, *gs_hist;   // NULL or [B][max_iter]
   double *ws_psi;           // [grid][3][2*nz*hw]  iterate rotation (cur / next / best), colour-split
-  double *ws_j;             // [grid][2*nz*hw]     J_raw -> J_phi, colour-split
-  double *ws_src;           // [grid][2*nz*hw]     right-hand side, colour-split
+  double *ws_src;           // [grid][2*nz*hw]     J_raw, then the right-hand side (rescaled in place), colour-split
   const double *seedJ, *cf, *mr, *rrow;
   const int *rowmask;
   double seed_sum_drdz;
@@ -909,6 +908,28 @@ __device__ __forceinline__ double grad_mag(const GradGeom &gg, double c, double 
   return hypot_glibc(gr, gz);
 }
 
+// J_raw of one point from its flux value (fusion_kernel.py:394-434): the per-point form of the S1 loop of the
+// resident kernel (same operations in the same order, so the two agree bit for bit).  Used to rebuild J_phi for the
+// output from the iterate the last source update saw - J is never stored per iteration.
+struct JrawK {
+  double psi_ax, denom, inv_denom;
+  bool hmode, same_prof;
+  MtanhK mkp, mkf;
+};
+__device__ __forceinline__ double jraw_point(const JrawK &K, double v, double r, double cfv) {
+  const double pn = ddiv_yf(dsub(v, K.psi_ax), K.denom, K.inv_denom);
+  double pr = 0.0, ff = 0.0;
+  if (pn >= 0.0 && pn < 1.0) {
+    if (K.hmode) {
+      pr = mtanh_res(pn, K.mkp);
+      ff = K.same_prof ? pr : mtanh_res(pn, K.mkf);
+    } else {
+      pr = ff = dsub(1.0, pn);
+    }
+  }
+  return dadd(dmul(0.5, dmul(r, pr)), dmul(0.5, dmul(cfv, ff)));
+}
+
 // block-wide broadcast of a value computed by thread 0 (through the scratch area)
 __device__ __forceinline__ double bcast_d(double v, int slot_off) {
   __syncthreads();
@@ -939,7 +960,6 @@ k_picard_resident(const __grid_constant__ RPlan plan, const __grid_constant__ Pi
   int *shi = reinterpret_cast<int *>(sh + 32);       // 32 ints (16 doubles)
   const int bslot = a.scratch_off + 48;              // broadcast slots
   double *wpsi = a.ws_psi + (size_t)blockIdx.x * 3 * planes;
-  double *wj = a.ws_j + (size_t)blockIdx.x * planes;
   double *wsrc = a.ws_src + (size_t)blockIdx.x * planes;
   const double n_all = (double)n, n_int = (double)(nz - 2) * (double)(nr - 2);
   const bool odd_nr = (nr & 1) != 0;  // then slot k = hw-1 holds only the (even) wall column
@@ -979,6 +999,7 @@ k_picard_resident(const __grid_constant__ RPlan plan, const __grid_constant__ Pi
     res_load_dense(a.psi + (size_t)b * n, xo, nz, nr, hw);
     int cur = 0, best = 0, nxt = 1;
     const bool do_seed = a.seed && fabs(ipb) >= 1e-12;
+    const double seed_sc = a.seed_sum_drdz > 0.0 ? __ddiv_rn(ipb, a.seed_sum_drdz) : 1.0;
     __syncthreads();
     if (a.seed) {
       for (int i = tid; i < planes; i += T) wpsi[2 * planes + i] = res_pool[xo + i];
@@ -987,13 +1008,11 @@ k_picard_resident(const __grid_constant__ RPlan plan, const __grid_constant__ Pi
 
     // ---- seed: Gaussian source scaled to Ip, 50 sanitised/clipped Jacobi steps (iterative_solver.py:384-410)
     if (do_seed) {
-      const double sc = a.seed_sum_drdz > 0.0 ? __ddiv_rn(ipb, a.seed_sum_drdz) : 1.0;
+      const double sc = seed_sc;
       for (int iz = warp; iz < nz; iz += nw)
         for (int ir = lane; ir < nr; ir += 32) {
           const double j = dmul(a.seedJ[iz * nr + ir], sc);
-          const int o = split_index(nz, hw, iz, ir);
-          wj[o] = j;
-          wsrc[o] = dmul(a.mr[ir], j);
+          wsrc[split_index(nz, hw, iz, ir)] = dmul(a.mr[ir], j);
         }
       __syncthreads();
       int p0 = xo, p1 = xo + ps, pt = a.tplane_off;  // colour-0 plane, colour-1 plane, spare
@@ -1055,10 +1074,7 @@ k_picard_resident(const __grid_constant__ RPlan plan, const __grid_constant__ Pi
       // 50 swaps: colour 0 is back in its home plane
     }
     if (a.external && !do_seed) {  // no seed ran: the loop's source is identically zero (J_phi = 0)
-      for (int i = tid; i < planes; i += T) {
-        wj[i] = 0.0;
-        wsrc[i] = 0.0;
-      }
+      for (int i = tid; i < planes; i += T) wsrc[i] = 0.0;
     }
     // current iterate -> workspace slot `cur`
     __syncthreads();
@@ -1066,6 +1082,9 @@ k_picard_resident(const __grid_constant__ RPlan plan, const __grid_constant__ Pi
     __syncthreads();
 
     int status = 0, iters = 0;
+    // J_phi is rebuilt for the output from (iterate slot, axis/boundary flux, scale) of the LAST source update
+    int j_slot = -1;
+    bool j_ok = false;
     double diff_best = 1e9, gs_best = INFINITY, gs_last = INFINITY, diff_last = 0.0, scale = 0.0;
     double psi_ax = 0.0, psi_b = 0.0, t_izax = 0, t_irax = 0, t_izx = 0, t_irx = 0, t_found = 0;
 
@@ -1199,6 +1218,7 @@ k_picard_resident(const __grid_constant__ RPlan plan, const __grid_constant__ Pi
       if (fabs(denom) < 1e-9) denom = 1e-9;
       const double inv_denom = __ddiv_rn(1.0, denom);
       const bool hmode = a.prof.hmode != 0;
+      j_slot = cur;  // the planes hold a copy of wpsi[cur]
       double acc = 0.0;
       GSB_SLOT_LOOP_BEGIN()
         const double pn_e = ddiv_yf(dsub(res_pool[xo + pa], psi_ax), denom, inv_denom);
@@ -1223,11 +1243,11 @@ k_picard_resident(const __grid_constant__ RPlan plan, const __grid_constant__ Pi
         }
         // J_raw = 0.5*(R*p) + 0.5*((1/(mu0 R))*ff)      (fusion_kernel.py:430-434)
         const double je = dadd(dmul(0.5, dmul(__ldg(a.rrow + 2 * k), pr_e)), dmul(0.5, dmul(__ldg(a.cf + 2 * k), ff_e)));
-        __stcg(wj + pa, je);
+        __stcg(wsrc + pa, je);  // J_raw parks in the right-hand-side plane until S2 rescales it in place
         acc += je;
         if (has_odd) {
           const double jo = dadd(dmul(0.5, dmul(__ldg(a.rrow + 2 * k + 1), pr_o)), dmul(0.5, dmul(__ldg(a.cf + 2 * k + 1), ff_o)));
-          __stcg(wj + pb, jo);
+          __stcg(wsrc + pb, jo);
           acc += jo;
         }
       GSB_SLOT_LOOP_END()
@@ -1237,6 +1257,7 @@ k_picard_resident(const __grid_constant__ RPlan plan, const __grid_constant__ Pi
       const double icur = dmul(dmul(jsum, a.dr), a.dz);
       const bool ok = fabs(icur) > 1e-9;
       scale = ok ? __ddiv_rn(ipb, icur) : 0.0;
+      j_ok = ok;
       {  // batches of four slots: all loads of a batch are in flight before the first use
         int e = tid, iz = iz_first, k = k_first;
         while (e < nslot) {
@@ -1249,8 +1270,8 @@ k_picard_resident(const __grid_constant__ RPlan plan, const __grid_constant__ Pi
             vok[u] = e < nslot;
             vpa[u] = par_ * ps + e, vpb[u] = (1 - par_) * ps + e, vk[u] = k;
             vho[u] = odd_nr ? (k < hw - 1) : true;
-            vje[u] = vok[u] ? __ldcg(wj + vpa[u]) : 0.0;
-            vjo[u] = (vok[u] && vho[u]) ? __ldcg(wj + vpb[u]) : 0.0;
+            vje[u] = vok[u] ? __ldcg(wsrc + vpa[u]) : 0.0;
+            vjo[u] = (vok[u] && vho[u]) ? __ldcg(wsrc + vpb[u]) : 0.0;
             e += T, k += step_k, iz += step_z;
             if (k >= hw) k -= hw, ++iz;
           }
@@ -1258,11 +1279,9 @@ k_picard_resident(const __grid_constant__ RPlan plan, const __grid_constant__ Pi
           for (int u = 0; u < 4; ++u) {
             if (vok[u]) {
               const double je = ok ? dmul(vje[u], scale) : 0.0;
-              __stcg(wj + vpa[u], je);
               __stcg(wsrc + vpa[u], dmul(__ldg(a.mr + 2 * vk[u]), je));
               if (vho[u]) {
                 const double jo = ok ? dmul(vjo[u], scale) : 0.0;
-                __stcg(wj + vpb[u], jo);
                 __stcg(wsrc + vpb[u], dmul(__ldg(a.mr + 2 * vk[u] + 1), jo));
               }
             }
@@ -1437,13 +1456,25 @@ k_picard_resident(const __grid_constant__ RPlan plan, const __grid_constant__ Pi
     // ---- results: colour-split workspace -> dense outputs
     {
       const double *fin = wpsi + (size_t)cur * planes;
+      const double *jsrc = wpsi + (size_t)(j_slot >= 0 ? j_slot : 0) * planes;
+      JrawK jk;  // psi_ax / psi_b still hold the values the last source update used
+      jk.psi_ax = psi_ax;
+      jk.denom = dsub(psi_b, psi_ax);
+      if (fabs(jk.denom) < 1e-9) jk.denom = 1e-9;
+      jk.inv_denom = __ddiv_rn(1.0, jk.denom);
+      jk.hmode = a.prof.hmode != 0, jk.same_prof = same_prof, jk.mkp = mkp, jk.mkf = mkf;
       double *po = a.psi + (size_t)b * n;
       double *jo = a.jphi + (size_t)b * n;
       for (int iz = warp; iz < nz; iz += nw)
         for (int ir = lane; ir < nr; ir += 32) {
           const int o = split_index(nz, hw, iz, ir);
           po[iz * nr + ir] = fin[o];
-          jo[iz * nr + ir] = wj[o];
+          double j;
+          if (j_slot >= 0)  // J_raw(psi of the last source update) * Ip/I, exactly as S1 / S2 formed it
+            j = j_ok ? dmul(jraw_point(jk, __ldcg(jsrc + o), __ldg(a.rrow + ir), __ldg(a.cf + ir)), scale) : 0.0;
+          else              // no source update ran (external_profile_mode): the seed's J_phi, or zero without a seed
+            j = do_seed ? dmul(a.seedJ[iz * nr + ir], seed_sc) : 0.0;
+          jo[iz * nr + ir] = j;
         }
       if (threadIdx.x == 0 && a.summary) {
         double *o = a.summary + (size_t)b * 16;
@@ -1776,7 +1807,7 @@ static int picard_resident_launch(gsb_ctx *ctx, const gsb_picard_params *p, doub
   const RLevel &c1 = plan.lev[1];
   if (4 * c1.nz * c1.hw < nz * hw) return GSB_ESTATE;
   gsb_picard_ws *w = ctx->picard;
-  const size_t planes = (size_t)2 * nz * hw, per_cta = 5 * planes;
+  const size_t planes = (size_t)2 * nz * hw, per_cta = 4 * planes;  // three iterate slots + the right-hand side
   const int grid = std::min(batch, ctx->num_sms);
   if (w->res_grid < grid) {
     if (w->res_ws) cudaFree(w->res_ws);
@@ -1795,8 +1826,7 @@ static int picard_resident_launch(gsb_ctx *ctx, const gsb_picard_params *p, doub
   a.hist = hist_dev;
   a.gs_hist = gs_hist_dev;
   a.ws_psi = w->res_ws;
-  a.ws_j = w->res_ws + (size_t)w->res_grid * 3 * planes;
-  a.ws_src = a.ws_j + (size_t)w->res_grid * planes;
+  a.ws_src = w->res_ws + (size_t)w->res_grid * 3 * planes;
   a.seedJ = w->seedJ;
   a.cf = w->cf;
   a.mr = w->mr;
