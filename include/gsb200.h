@@ -161,7 +161,7 @@ typedef struct gsb_picard_params {
   double tol;                  /* solver.convergence_threshold */
   double alpha;                /* solver.relaxation_factor (default 0.1) */
   double omega;                /* solver.sor_omega (default 1.6) */
-  int method;                  /* 0 multigrid (default), 1 sor, 2 jacobi */
+  int method;                  /* 0 multigrid (default), 1 sor, 2 jacobi, 3 anderson (SOR sweep + Anderson mixing) */
   int require_gs_residual;     /* solver.require_gs_residual */
   double gs_tol;               /* solver.gs_residual_threshold */
   int saddle;                  /* solver.xpoint_use_saddle_detection */
@@ -173,6 +173,9 @@ typedef struct gsb_picard_params {
   int external_profile;        /* 1: external_profile_mode (fusion_kernel_newton_solver.py:509) - J_phi is NOT updated
                                   from psi inside the loop; every iteration solves with the source left by the seed
                                   (_seed_plasma overwrites J_phi before the loop, also in this mode) */
+  int anderson_depth;          /* method 3: solver.anderson_depth (default 5), 0..8; the iterate is mixed on iterations
+                                  3, 6, 9, ... over the last min(depth, k+1) relaxed iterates
+                                  (fusion_kernel_iterative_solver.py:248-314, fusion_kernel_newton_solver.py:539-550) */
 } gsb_picard_params;
 
 /* a13+a14: batched Picard solve (solve_equilibrium, fusion_kernel_newton_solver.py:390-615).

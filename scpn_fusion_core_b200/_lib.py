@@ -28,7 +28,7 @@ class gsb_picard_params(ctypes.Structure):
         ("max_iterations", c_int), ("tol", c_double), ("alpha", c_double), ("omega", c_double),
         ("method", c_int), ("require_gs_residual", c_int), ("gs_tol", c_double), ("saddle", c_int),
         ("mu0", c_double), ("z_min", c_double), ("r_min", c_double), ("r_max", c_double),
-        ("seed", c_int), ("check_every", c_int), ("prof", gsb_profile), ("external_profile", c_int),
+        ("seed", c_int), ("check_every", c_int), ("prof", gsb_profile), ("external_profile", c_int), ("anderson_depth", c_int),
     ]
 
 

@@ -51,6 +51,11 @@ struct gsb_picard_ws {
   // private per-CTA workspace of the persistent resident solve: [grid][5 * 2*nz*hw] (colour-split)
   double *res_ws = nullptr;
   int res_grid = 0;
+  // Anderson mixing (method 3), allocated on first use: iterate / residual rings [cap][and_slots][n], Gram partials,
+  // coefficients, fallback flags
+  double *and_psi = nullptr, *and_res = nullptr, *and_part = nullptr, *and_alpha = nullptr;
+  int *and_fb = nullptr;
+  int and_slots = 0;
 };
 
 namespace gsb {
@@ -737,6 +742,244 @@ __global__ void k_decide(PicardState s, const double *__restrict__ rpart, int P,
     s.active[b] = 0;
   } else {
     atomicAdd(counter, 1);
+  }
+}
+
+// ---------------------------------------------------------------------------- A  (solver_method "anderson")
+// Anderson mixing of the relaxed Picard iterates (fusion_kernel_iterative_solver.py:248-314, called from
+// fusion_kernel_newton_solver.py:539-550): every iteration pushes (Psi_relaxed, Psi_new - Psi_relaxed) into a ring of
+// `m` slots; on iterations k = 3, 6, 9, ... the iterate is replaced by sum_j alpha_j Psi_j over the last
+// mk = min(m, k+1) entries, alpha from the 1e-10-regularised normal equations of the residual differences, walls reset
+// to the boundary map, and the GS residual of the iteration is taken of the MIXED state.  Every active equilibrium of a
+// solve is at the same iteration, but the decision "is this a mixing iteration" is taken on the device from s.iter so
+// that the launch sequence stays iteration-independent (CUDA-graph replay).
+// Not bit-identical to NumPy by construction: the reference forms the Gram matrix with BLAS (dF.T @ dF) and solves it
+// with LAPACK gesv, whose summation orders are not specified; here fixed trees + partial-pivot LU.
+constexpr int kAndMax = 8;                                           // largest supported mixing depth
+constexpr int kAndEnt = (kAndMax - 1) * kAndMax / 2 + (kAndMax - 1); // upper-triangular Gram entries + rhs
+constexpr int kAndPB = 16;                                           // partial blocks per equilibrium
+
+__device__ __forceinline__ bool and_mix_iter(int k) { return k >= 3 && k % 3 == 0; }  // len(history) >= 3 and k % 3 == 0
+__device__ __forceinline__ int and_mk(int m, int k) { return min(m, k + 1); }
+
+struct AndersonBufs {
+  double *psi, *res;   // [batch_cap][slots][n] rings
+  double *part;        // [batch_cap][kAndPB][kAndEnt]
+  double *alpha;       // [batch_cap][kAndMax]
+  int *fallback;       // [batch_cap] 1: the mixed iterate is the latest iterate (LinAlgError / |sum alpha| < 1e-12 / mk < 2)
+  int m, slots;
+};
+
+__global__ void __launch_bounds__(256)
+k_and_push(AndersonBufs a, Bufs bufs, const int *__restrict__ nxt, const int *__restrict__ iter,
+           const double *__restrict__ Wall, const double *__restrict__ ringall, int nz, int nr,
+           const int *__restrict__ active) {
+  const int b = blockIdx.y;
+  if (!active[b] || a.m < 2) return;
+  const size_t n = (size_t)nz * nr;
+  const int slot = iter[b] % a.slots;
+  const double *rel = bufs.p[nxt[b]] + b * n;
+  const double *W = Wall + b * n;
+  const double *ring = ringall + (size_t)b * ring_size(nz, nr);
+  double *hp = a.psi + ((size_t)b * a.slots + slot) * n, *hr = a.res + ((size_t)b * a.slots + slot) * n;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int iz = (int)(i / nr), ir = (int)(i - (size_t)iz * nr);
+    const double r = rel[i];
+    hp[i] = r;
+    hr[i] = dsub(wall_or(W, ring, nz, nr, iz, ir), r);  // Psi_new - Psi (relaxed), newton_solver.py:542
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_and_gram(AndersonBufs a, const int *__restrict__ iter, size_t n, const int *__restrict__ active) {
+  __shared__ double sh[32];
+  const int b = blockIdx.y;
+  if (!active[b]) return;
+  const int k = iter[b];
+  if (!and_mix_iter(k)) return;
+  const int mk = and_mk(a.m, k);
+  if (mk < 2) return;
+  const int d = mk - 1;
+  const double *col[kAndMax];
+#pragma unroll
+  for (int j = 0; j < kAndMax; ++j) {
+    const int slot = (k - mk + 1 + min(j, mk - 1)) % a.slots;  // oldest first; unused columns alias the last one
+    col[j] = a.res + ((size_t)b * a.slots + slot) * n;
+  }
+  double acc[kAndEnt];
+#pragma unroll
+  for (int e = 0; e < kAndEnt; ++e) acc[e] = 0.0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    double r[kAndMax], df[kAndMax - 1];
+#pragma unroll
+    for (int j = 0; j < kAndMax; ++j) r[j] = j < mk ? col[j][i] : 0.0;
+    const double last = col[kAndMax - 1][i];  // aliases column mk-1
+#pragma unroll
+    for (int j = 0; j < kAndMax - 1; ++j) df[j] = j < d ? dsub(r[j + 1], r[j]) : 0.0;  // np.diff(F, axis=1)
+    int e = 0;
+#pragma unroll
+    for (int p = 0; p < kAndMax - 1; ++p)
+#pragma unroll
+      for (int q = p; q < kAndMax - 1; ++q, ++e) acc[e] += df[p] * df[q];
+#pragma unroll
+    for (int p = 0; p < kAndMax - 1; ++p, ++e) acc[e] += df[p] * last;
+  }
+  double *o = a.part + ((size_t)b * kAndPB + blockIdx.x) * kAndEnt;
+#pragma unroll
+  for (int e = 0; e < kAndEnt; ++e) {
+    const double v = block_sum(acc[e], sh);
+    if (threadIdx.x == 0) o[e] = v;
+  }
+}
+
+// One thread per equilibrium: Gram assembly, + 1e-10 I, LU with partial pivoting (first largest |a_ik|, as idamax),
+// gamma, alpha (fusion_kernel_iterative_solver.py:289-303, np.sum restated for <= 8 values).
+__global__ void k_and_solve(AndersonBufs a, const int *__restrict__ iter, int n_part, int batch,
+                            const int *__restrict__ active) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch || !active[b]) return;
+  const int k = iter[b];
+  if (!and_mix_iter(k)) return;
+  const int mk = and_mk(a.m, k);
+  if (mk < 2) {
+    a.fallback[b] = 1;
+    return;
+  }
+  const int d = mk - 1;
+  double ent[kAndEnt];
+  for (int e = 0; e < kAndEnt; ++e) {
+    double v = 0.0;
+    for (int p = 0; p < n_part; ++p) v += a.part[((size_t)b * kAndPB + p) * kAndEnt + e];
+    ent[e] = v;
+  }
+  double A[kAndMax - 1][kAndMax - 1], x[kAndMax - 1];
+  int e = 0;
+  for (int p = 0; p < kAndMax - 1; ++p)
+    for (int q = p; q < kAndMax - 1; ++q, ++e)
+      if (q < d) A[p][q] = A[q][p] = ent[e];
+  for (int p = 0; p < kAndMax - 1; ++p, ++e)
+    if (p < d) x[p] = ent[e];
+  for (int p = 0; p < d; ++p) A[p][p] = dadd(A[p][p], 1e-10);
+  bool singular = false;
+  for (int c = 0; c < d && !singular; ++c) {
+    int piv = c;
+    double best = fabs(A[c][c]);
+    for (int r = c + 1; r < d; ++r)
+      if (fabs(A[r][c]) > best) {
+        best = fabs(A[r][c]);
+        piv = r;
+      }
+    if (A[piv][c] == 0.0) {
+      singular = true;  // gesv info > 0 -> numpy raises LinAlgError
+      break;
+    }
+    if (piv != c) {
+      for (int q = 0; q < d; ++q) {
+        const double t = A[c][q];
+        A[c][q] = A[piv][q];
+        A[piv][q] = t;
+      }
+      const double t = x[c];
+      x[c] = x[piv];
+      x[piv] = t;
+    }
+    const double rp = 1.0 / A[c][c];
+    for (int r = c + 1; r < d; ++r) {
+      const double l = A[r][c] * rp;
+      for (int q = c + 1; q < d; ++q) A[r][q] -= l * A[c][q];
+      x[r] -= l * x[c];
+    }
+  }
+  int fb = singular ? 1 : 0;
+  double al[kAndMax];
+  if (!singular) {
+    for (int r = d - 1; r >= 0; --r) {
+      double v = x[r];
+      for (int q = r + 1; q < d; ++q) v -= A[r][q] * x[q];
+      x[r] = v / A[r][r];
+    }
+    double gs = 0.0;
+    for (int j = 0; j < d; ++j) gs = dadd(gs, x[j]);  // np.sum of < 8 values: left to right from 0
+    for (int j = 0; j < d; ++j) al[j] = dsub(0.0, x[j]);
+    al[d] = dsub(1.0, gs);
+    double tot;
+    if (mk < 8) {
+      tot = 0.0;
+      for (int j = 0; j < mk; ++j) tot = dadd(tot, al[j]);
+    } else {  // np.sum of exactly 8 values: eight accumulators combined as a tree
+      tot = dadd(dadd(dadd(al[0], al[1]), dadd(al[2], al[3])), dadd(dadd(al[4], al[5]), dadd(al[6], al[7])));
+    }
+    if (fabs(tot) < 1e-12) fb = 1;  // (a NaN sum compares false here as in the reference and mixes NaN through)
+    if (!fb)
+      for (int j = 0; j < mk; ++j) a.alpha[(size_t)b * kAndMax + j] = __ddiv_rn(al[j], tot);
+  }
+  a.fallback[b] = fb;
+}
+
+// mixed = sum_j alpha_j Psi_j (accumulated from zeros in history order, :306-312), walls <- boundary map
+// (_apply_boundary_conditions); the fallback keeps the relaxed iterate and only resets its walls.
+__global__ void __launch_bounds__(256)
+k_and_mix(AndersonBufs a, Bufs bufs, const int *__restrict__ nxt, const int *__restrict__ iter,
+          const double *__restrict__ ringall, int nz, int nr, const int *__restrict__ active) {
+  const int b = blockIdx.y;
+  if (!active[b]) return;
+  const int k = iter[b];
+  if (!and_mix_iter(k)) return;
+  const size_t n = (size_t)nz * nr;
+  const int mk = and_mk(a.m, k);
+  const bool fb = a.fallback[b] != 0;
+  const double *ring = ringall + (size_t)b * ring_size(nz, nr);
+  double *out = bufs.p[nxt[b]] + b * n;
+  const double *col[kAndMax];
+  double al[kAndMax];
+#pragma unroll
+  for (int j = 0; j < kAndMax; ++j) {
+    const int slot = (k - mk + 1 + min(j, max(mk - 1, 0))) % a.slots;
+    col[j] = a.psi + ((size_t)b * a.slots + slot) * n;
+    al[j] = (!fb && j < mk) ? a.alpha[(size_t)b * kAndMax + j] : 0.0;
+  }
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int iz = (int)(i / nr), ir = (int)(i - (size_t)iz * nr);
+    if (iz == 0 || iz == nz - 1 || ir == 0 || ir == nr - 1) {
+      out[i] = wall_or(nullptr, ring, nz, nr, iz, ir);
+    } else if (!fb) {
+      double v = 0.0;
+#pragma unroll
+      for (int j = 0; j < kAndMax; ++j)
+        if (j < mk) v = dadd(v, dmul(al[j], col[j][i]));
+      out[i] = v;
+    }
+  }
+}
+
+// GS residual statistics of the mixed iterate (newton_solver.py:552 sees self.Psi AFTER the mixing step): overwrites
+// the (max |r|, sum r^2) entries k_relax left for the relaxed iterate, in the same P partial slots k_decide adds up.
+__global__ void __launch_bounds__(256)
+k_and_gs(LevelGeom g, Bufs bufs, const int *__restrict__ nxt, const int *__restrict__ iter,
+         const double *__restrict__ srcall, double *__restrict__ rpart, const int *__restrict__ active) {
+  __shared__ double sh[32];
+  const int b = blockIdx.y, p = blockIdx.x;
+  if (!active[b] || !and_mix_iter(iter[b])) return;
+  const int nz = g.nz, nr = g.nr;
+  const size_t n = (size_t)nz * nr;
+  const double *f = bufs.p[nxt[b]] + b * n;
+  const double *src = srcall + b * n;
+  const size_t n_in = (size_t)(nz - 2) * (nr - 2);
+  double rmax = 0.0, rsq = 0.0;
+  for (size_t q = (size_t)p * blockDim.x + threadIdx.x; q < n_in; q += (size_t)gridDim.x * blockDim.x) {
+    const int iz = 1 + (int)(q / (nr - 2)), ir = 1 + (int)(q % (nr - 2));
+    const size_t o = (size_t)iz * nr + ir;
+    const double r = dsub(gs_apply(g, ir, f[o], f[o + 1], f[o - 1], f[o - nr], f[o + nr]), src[o]);
+    rmax = fmax(rmax, fabs(r));
+    rsq += r * r;
+  }
+  rmax = block_max(rmax, sh);
+  __syncthreads();
+  rsq = block_sum(rsq, sh);
+  if (threadIdx.x == 0) {
+    double *o = rpart + ((size_t)b * kPT + p) * kRW;
+    o[2] = rmax;
+    o[3] = rsq;
   }
 }
 
@@ -1876,7 +2119,8 @@ void gsb_picard_ws_free(gsb_ctx *ctx) {
   gsb_picard_ws *w = ctx->picard;
   if (!w) return;
   void *ptrs[] = {w->buf1, w->buf2, w->W, w->source, w->ring, w->tpart, w->spart, w->rpart,
-                  w->seedJ, w->cf, w->mr, w->rowmask, w->ints, w->dbls, w->res_ws, w->mrows, w->cand};
+                  w->seedJ, w->cf, w->mr, w->rowmask, w->ints, w->dbls, w->res_ws, w->mrows, w->cand,
+                  w->and_psi, w->and_res, w->and_part, w->and_alpha, w->and_fb};
   for (void *q : ptrs)
     if (q) cudaFree(q);
   delete w;
@@ -1971,7 +2215,9 @@ static int picard_solve_impl(gsb_ctx *ctx, const gsb_picard_params *p, double *p
   GSB_REQUIRE(ctx && p && psi_dev && bc_dev && ip_dev && jphi_dev && summary_dev, "gsb_picard_solve: NULL argument");
   GSB_REQUIRE(batch >= 1 && batch <= ctx->batch_cap, "gsb_picard_solve: batch outside [1, batch_cap]");
   GSB_REQUIRE(p->max_iterations >= 1, "gsb_picard_solve: max_iterations must be >= 1");
-  GSB_REQUIRE(p->method >= 0 && p->method <= 2, "gsb_picard_solve: unknown method");
+  GSB_REQUIRE(p->method >= 0 && p->method <= 3, "gsb_picard_solve: unknown method");
+  GSB_REQUIRE(p->method != 3 || (p->anderson_depth >= 0 && p->anderson_depth <= kAndMax),
+              "gsb_picard_solve: anderson_depth outside [0, 8]");
   GSB_REQUIRE(std::isfinite(p->omega) && p->omega >= 1.0 && p->omega < 2.0,
               "omega must be finite and satisfy 1.0 <= omega < 2.0");
   GSB_REQUIRE(!p->require_gs_residual || p->gs_tol > 0.0, "solver.gs_residual_threshold must be > 0");
@@ -2037,6 +2283,31 @@ static int picard_solve_impl(gsb_ctx *ctx, const gsb_picard_params *p, double *p
     }
   }
 
+  AndersonBufs mixb{};
+  if (p->method == 3) {  // depth < 2 never mixes (mk < 2): the "mixed" iterate is the relaxed one with its walls reset
+    mixb.m = p->anderson_depth;
+    mixb.slots = std::max(mixb.m, 1);
+    if (mixb.m >= 2 && w->and_slots < mixb.slots) {
+      if (w->and_psi) cudaFree(w->and_psi);
+      if (w->and_res) cudaFree(w->and_res);
+      w->and_psi = w->and_res = nullptr;
+      w->and_slots = 0;
+      const size_t bytes = (size_t)w->cap * mixb.slots * n * sizeof(double);
+      GSB_CUDA(cudaMalloc(&w->and_psi, bytes));
+      GSB_CUDA(cudaMalloc(&w->and_res, bytes));
+      w->and_slots = mixb.slots;
+    }
+    if (!w->and_part) {
+      GSB_CUDA(cudaMalloc(&w->and_part, (size_t)w->cap * kAndPB * kAndEnt * sizeof(double)));
+      GSB_CUDA(cudaMalloc(&w->and_alpha, (size_t)w->cap * kAndMax * sizeof(double)));
+      GSB_CUDA(cudaMalloc(&w->and_fb, (size_t)w->cap * sizeof(int)));
+    }
+    mixb.psi = w->and_psi;
+    mixb.res = w->and_res;
+    mixb.part = w->and_part;
+    mixb.alpha = w->and_alpha;
+    mixb.fallback = w->and_fb;
+  }
   const double oma = 1.0 - p->alpha;
   const RelaxPlan rplan = relax_plan(nz, nr);
   const int check_every = p->check_every > 0 ? p->check_every : 8;
@@ -2066,7 +2337,7 @@ static int picard_solve_impl(gsb_ctx *ctx, const gsb_picard_params *p, double *p
       GSB_LAUNCH_CHECK();
       int r2 = vcycle_launch(ctx, w->W, n, w->source, batch, p->omega, 3, 3, s.active, st);
       if (r2) return r2;
-    } else if (p->method == 1) {
+    } else if (p->method == 1 || p->method == 3) {  // "anderson" uses the SOR sweep (iterative_solver.py:376)
       k_copy_from_cur<<<dim3(copy_blocks, batch), 256, 0, st>>>(bufs, s.cur, n, w->W, 1, s.active);
       GSB_LAUNCH_CHECK();
       int r2 = smooth_launch(g, w->W, n, w->source, n, batch, p->omega, 1, 1, s.active, st);
@@ -2079,6 +2350,21 @@ static int picard_solve_impl(gsb_ctx *ctx, const gsb_picard_params *p, double *p
     k_relax<<<dim3(rplan.n_cc * rplan.n_rb, batch), rplan.cc, 0, st>>>(g, bufs, s.cur, s.nxt, w->W, w->ring, w->source, p->alpha,
                                                                       oma, w->rpart, s.active, rplan);
     GSB_LAUNCH_CHECK();
+    if (p->method == 3) {  // every kernel decides on the device whether this is a mixing iteration
+      const int blocks = (int)std::min<size_t>((n + 255) / 256, 256);
+      k_and_push<<<dim3(blocks, batch), 256, 0, st>>>(mixb, bufs, s.nxt, s.iter, w->W, w->ring, nz, nr, s.active);
+      GSB_LAUNCH_CHECK();
+      if (mixb.m >= 2) {
+        k_and_gram<<<dim3(kAndPB, batch), 256, 0, st>>>(mixb, s.iter, n, s.active);
+        GSB_LAUNCH_CHECK();
+      }
+      k_and_solve<<<(batch + 63) / 64, 64, 0, st>>>(mixb, s.iter, kAndPB, batch, s.active);
+      GSB_LAUNCH_CHECK();
+      k_and_mix<<<dim3(blocks, batch), 256, 0, st>>>(mixb, bufs, s.nxt, s.iter, w->ring, nz, nr, s.active);
+      GSB_LAUNCH_CHECK();
+      k_and_gs<<<dim3(rplan.n_cc * rplan.n_rb, batch), 256, 0, st>>>(g, bufs, s.nxt, s.iter, w->source, w->rpart, s.active);
+      GSB_LAUNCH_CHECK();
+    }
     if (poll) GSB_CUDA(cudaMemsetAsync(ctx->counter, 0, sizeof(int), st));
     k_decide<<<(batch + 127) / 128, 128, 0, st>>>(s, w->rpart, rplan.n_cc * rplan.n_rb, (double)n, (double)(nz - 2) * (double)(nr - 2), p->tol,
                                                   p->require_gs_residual, p->gs_tol, p->max_iterations, hist_dev,

@@ -8,8 +8,8 @@ meaning, result-dict keys and error behaviour.  Every numerical step runs in lib
 equilibria (UQ / design sweeps) through the same kernels in one launch sequence.
 
 The free-boundary layer (coil Green's functions, shape optimisation, probe reconstruction) lives in
-``free_boundary.py``.  Out of scope here: ``solver_method`` in {"newton", "anderson",
-"rust_multigrid"} raises ``NotImplementedError``.
+``free_boundary.py``.  Out of scope here: ``solver_method`` in {"newton", "rust_multigrid"} raises
+``NotImplementedError`` ("anderson" - SOR sweep + Anderson mixing - runs on the device since r2).
 """
 from __future__ import annotations
 
@@ -32,7 +32,7 @@ _mg = __import__("importlib").import_module(__package__ + ".multigrid_solve")  #
 logger = logging.getLogger(__name__)
 
 MAX_CONFIG_BYTES = 10 * 1024 * 1024
-_METHODS = {"multigrid": 0, "sor": 1, "jacobi": 2}
+_METHODS = {"multigrid": 0, "sor": 1, "jacobi": 2, "anderson": 3}
 _PED_KEYS = ("ped_top", "ped_width", "ped_height", "core_alpha")
 _MU0_SI = 4e-7 * np.pi
 
@@ -192,6 +192,12 @@ class _GridMixin:
         p.check_every = int(so.get("gpu_check_every", 8))
         p.prof = _profile_struct(self._hmode, self.ped_params_p, self.ped_params_ff)
         p.external_profile = 1 if bool(getattr(self, "external_profile_mode", False)) else 0
+        p.anderson_depth = 0
+        if method == "anderson":  # fusion_kernel_newton_solver.py:481; a depth below 2 never mixes (mk < 2)
+            depth = int(so.get("anderson_depth", 5))
+            if depth > 8:
+                raise NotImplementedError("solver.anderson_depth > 8 is outside the B200 hot path")
+            p.anderson_depth = max(depth, 1)
         return p
 
     # Green's tables are geometry-only: build once per (coil set, flavour)

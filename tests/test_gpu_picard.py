@@ -260,7 +260,7 @@ def test_external_profile_mode_and_nonfinite_x_point(pkg):
 
 def test_unsupported_methods_are_loud(pkg):
     z = golden("solves")
-    for m in ("newton", "anderson", "rust_multigrid"):
+    for m in ("newton", "rust_multigrid"):
         cfg = golden_cfg(z, "iter65")
         cfg["solver"]["solver_method"] = m
         with pytest.raises(NotImplementedError):

@@ -305,6 +305,40 @@ def test_anderson_method(tag):
     np.testing.assert_allclose(mixed, np.full((4, 5), 7.0 / 3.0), rtol=1e-8)
 
 
+def test_anderson_val33_is_summation_order_sensitive(monkeypatch):
+    """Why the 1000-iteration 33^2 anderson fixture cannot be an end-state bar for ANY second implementation: NumPy
+    itself, with nothing changed but the accumulation precision of the mixing Gram matrix, follows the fixture to 1e-8
+    for 60 iterations and has left it by > 1e-6 at iteration 120 (the run is non-contractive; deviations grow ~10x per
+    10 iterations).  tests/test_gpu_anderson.py therefore compares the first 60 iterations of that run."""
+    import json
+
+    def mix_longdouble(psi_hist, res_hist, m=5):
+        mk = min(m, len(res_hist))
+        F = np.column_stack([r.ravel() for r in res_hist[-mk:]])
+        dl = np.diff(F, axis=1).astype(np.longdouble)
+        gram = (dl.T @ dl).astype(np.float64) + 1e-10 * np.eye(mk - 1)
+        gamma = np.linalg.solve(gram, (dl.T @ F[:, -1].astype(np.longdouble)).astype(np.float64))
+        a = np.zeros(mk)
+        a[-1] = 1.0 - np.sum(gamma)
+        a[:-1] -= gamma
+        a /= np.sum(a)
+        mixed = np.zeros_like(psi_hist[-1])
+        for j, p in enumerate(psi_hist[-mk:]):
+            mixed += a[j] * p
+        return mixed
+
+    if np.finfo(np.longdouble).eps >= np.finfo(np.float64).eps:
+        pytest.skip("no extended precision on this platform")
+    z = golden("anderson")
+    cfg = json.loads(str(z["val33_cfg"]))
+    cfg["solver"]["max_iterations"] = 120
+    monkeypatch.setattr(G, "anderson_mix", mix_longdouble)
+    h = np.array(G.picard_solve(G.PicardProblem(cfg))["residual_history"])
+    dev = np.abs(h - z["val33_hist"][:120]) / z["val33_hist"][:120]
+    assert dev[:60].max() < 1e-7
+    assert dev.max() > 1e-6
+
+
 def test_hpc_cpp_arithmetic():
     """oracle.hpc_run_step vs the compiled reference solver.cpp (FMA contraction allowed there)."""
     z = golden("hpc_solver")
