@@ -36,10 +36,6 @@ struct SweepArgs {
   const int *active;
 };
 
-__device__ __forceinline__ void cp_async8(void *smem, const void *gmem) {
-  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem) : "memory");
-}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
@@ -49,12 +45,38 @@ __device__ __forceinline__ void cp_async_wait() {
 // P0 = (zl + par_off + cl) & 1 of the warp's tile, hoisted into a template parameter by the
 // dispatching kernel below: with the step loop unrolled over one ring period every ring slot and
 // every colour parity is a compile-time constant (no address arithmetic in the loop body).
-template <int NST, int P0>
-__device__ __forceinline__ void sweep_warp_body(const SweepArgs &a, double *ring_p, double *ring_s, int lane, int zl,
+// 32-bit shared-window accesses (the ring addresses rotate through registers, so the compiler could not prove the
+// address space of a generic pointer).  asm volatile keeps the program order of ring reads and writes.
+__device__ __forceinline__ double lds64(unsigned a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts64(unsigned a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v)); }
+__device__ __forceinline__ void cp_async8s(unsigned s, const void *gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem) : "memory");
+}
+
+// One warp, one tile.  P0 = (zl + par_off + cl) & 1 of the tile, hoisted into a template parameter by the dispatching
+// kernel below, UNR = steps per unrolled loop body (even, so every colour parity in the body is a compile-time constant).
+//
+// r1 unrolled the step loop over the whole ring period (16 steps): every ring slot was a compile-time constant, but the
+// body of the 6-stage kernel was 4 150 SASS instructions per parity variant (133 KB for both) with every warp of an SM
+// somewhere else in it, and ncu's top stall reason was `no_instruction` - instruction-cache misses (2.7 of 7.5 stalled
+// warp-cycles per issue, profiles/r2_sweep_icache.md).  Now the body is UNR = 2 steps and the sixteen slot addresses live
+// in sixteen registers that ROTATE by UNR after every body (A[i] = shared address of the slot that holds relative row
+// base - 11 + i): the wrap-around of the ring costs UNR register moves per step and no address arithmetic, row pointers
+// into global memory advance by one row per step instead of being recomputed.
+template <int NST, int P0, int UNR>
+__device__ __forceinline__ void sweep_warp_body(const SweepArgs &a, double *ring, int lane, int zl,
                                                 int zh, int z0, int z1, int cl, int wb, int c0, int c1,
                                                 const double *gin, const double *gsrc, double *gout) {
   constexpr int NRING = 16;            // rows qi-2(NST-1)-1 .. qi+PF live at step qi
   constexpr int PF = NRING - 2 * NST;  // prefetch distance in rows (deeper for the shorter steps of small NST)
+  constexpr unsigned SLOT = 64 * 8;    // bytes per ring slot: [even half row][odd half row] of 32 doubles
+  constexpr unsigned HALF = 32 * 8;
+  constexpr unsigned SRC = NRING * SLOT;  // the source ring follows the psi ring
+  static_assert(UNR % 2 == 0 && NRING % UNR == 0, "the unroll factor must keep the colour parity compile-time");
   const int nr = a.nr;
   const int xe = 2 * lane, xo = 2 * lane + 1;  // the lane's columns inside the strip
   const bool have_e = xe < wb, have_o = xo < wb;
@@ -63,55 +85,61 @@ __device__ __forceinline__ void sweep_warp_body(const SweepArgs &a, double *ring
   const double ae_e = have_e ? a.a_e[cl + xe] : 0.0, aw_e = have_e ? a.a_w[cl + xe] : 0.0;
   const double ae_o = have_o ? a.a_e[cl + xo] : 0.0, aw_o = have_o ? a.a_w[cl + xo] : 0.0;
   const double a_ns = a.a_ns, a_c = a.a_c, inv_a_c = a.inv_a_c, omega = a.omega, omw = a.omw;
-  double *rp = ring_p + lane;  // ring slot of row zl + q is q & (NRING-1); element [slot][half][lane]
-  double *rs = ring_s + lane;
+  const unsigned rb = (unsigned)__cvta_generic_to_shared(ring) + (unsigned)lane * 8u;  // slot 0, even half, this lane
   const int nrows = zh - zl;   // loaded rows, relative index q = r - zl in [0, nrows)
+  const size_t rowb = (size_t)nr * sizeof(double);
 
-  auto load_row = [&](int q, int slot) {  // asynchronous copy of row zl+q (psi and source) into `slot`
-    if (q < nrows) {
-      const double *pr = gin + (size_t)(zl + q) * nr + cl;
-      const double *sr = gsrc + (size_t)(zl + q) * nr + cl;
+  // asynchronous copy of one row (psi and source) into the slot at shared address `sa`; `pr` / `sr` point at this
+  // lane's even column of that row
+  auto load_row = [&](bool row_ok, unsigned sa, const char *pr, const char *sr) {
+    if (row_ok) {
       if (have_e) {
-        cp_async8(rp + (slot * 2) * 32, pr + xe);
-        cp_async8(rs + (slot * 2) * 32, sr + xe);
+        cp_async8s(sa, pr);
+        cp_async8s(sa + SRC, sr);
       }
       if (have_o) {
-        cp_async8(rp + (slot * 2 + 1) * 32, pr + xo);
-        cp_async8(rs + (slot * 2 + 1) * 32, sr + xo);
+        cp_async8s(sa + HALF, pr + 8);
+        cp_async8s(sa + SRC + HALF, sr + 8);
       }
     }
     cp_async_commit();
   };
+  const char *pin = (const char *)(gin + (size_t)zl * nr + cl + xe);
+  const char *psr = (const char *)(gsrc + (size_t)zl * nr + cl + xe);
 #pragma unroll
-  for (int q = 0; q <= PF; ++q) load_row(q, q);
+  for (int q = 0; q <= PF; ++q) load_row(q < nrows, rb + q * SLOT, pin + q * rowb, psr + q * rowb);
+  pin += (size_t)(PF + 1) * rowb;  // the row step qi = 1 prefetches
+  psr += (size_t)(PF + 1) * rowb;
   cp_async_wait<PF - 2>();  // rows 0 .. 2 have landed
   __syncwarp();
 
-  const int q_end = (nrows - 2) + 2 * (NST - 1);  // last step (relative row of stage 0)
-  for (int base = 0; base <= q_end; base += NRING) {
+  unsigned A[NRING];  // A[i]: slot of relative row base - 11 + i, i.e. slot (base + i + 5) & 15
 #pragma unroll
-    for (int u = 0; u < NRING; ++u) {
+  for (int i = 0; i < NRING; ++i) A[i] = rb + ((i + 5) & (NRING - 1)) * SLOT;
+  // row written back at step qi is relative row qi - 2(NST-1); pointer at this lane's even column, for qi = 1
+  char *pout = (char *)(gout + cl + xe) + ((ptrdiff_t)zl + 1 - 2 * (NST - 1)) * (ptrdiff_t)rowb;
+  const unsigned w_lo = (unsigned)(z0 - zl + 2 * (NST - 1)), w_n = (unsigned)(z1 - z0);  // write iff qi - w_lo < w_n (unsigned)
+  const unsigned q_hi = (unsigned)(nrows - 3);  // a stage row q is updated iff (unsigned)(q - 1) <= q_hi
+  const int q_end = (nrows - 2) + 2 * (NST - 1);  // last step (relative row of stage 0)
+  for (int base = 0; base <= q_end; base += UNR) {
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
       const int qi = base + u;  // stage 0 is at relative row qi (row 0 is never updated)
       if (qi >= 1 && qi <= q_end) {
         double W[NST], E[NST], S[NST], N[NST], O[NST], F[NST], V[NST];
-        bool on[NST];
-        // ---- operands of every stage (stage t = colour pass t at relative row qi - 2t)
+        // ---- operands of every stage (stage t = colour pass t at relative row qi - 2t = ring index 11 + u - 2t)
 #pragma unroll
         for (int t = 0; t < NST; ++t) {
-          constexpr int M = NRING - 1;
-          const int q = qi - 2 * t;
-          const int hx = (t + u + P0) & 1;           // column parity of this pass's points in that row
-          const int slot = (u - 2 * t) & M, sl_s = (u - 2 * t - 1) & M, sl_n = (u - 2 * t + 1) & M;  // compile time
-          on[t] = (q >= 1 && q <= nrows - 2) && (hx ? upd_o : upd_e);
-          const double *me = rp + (slot * 2 + hx) * 32;        // own half row
-          const double *ot = rp + (slot * 2 + (1 - hx)) * 32;  // the other colour's half row
-          // unconditional loads (always inside the padded ring): no branches, so the 2S stages overlap
-          W[t] = hx ? ot[0] : ot[-1];
-          E[t] = hx ? ot[1] : ot[0];
-          S[t] = rp[(sl_s * 2 + hx) * 32];
-          N[t] = rp[(sl_n * 2 + hx) * 32];
-          O[t] = me[0];
-          F[t] = rs[(slot * 2 + hx) * 32];
+          const int hx = (t + u + P0) & 1;  // column parity of this pass's points in that row (compile time)
+          const unsigned me = A[(11 + u - 2 * t) & (NRING - 1)] + hx * HALF;        // own half row
+          const unsigned ot = A[(11 + u - 2 * t) & (NRING - 1)] + (1 - hx) * HALF;  // the other colour's half row
+          // unconditional loads (always inside the ring): no branches, so the 2S stages overlap
+          W[t] = lds64(hx ? ot : ot - 8);
+          E[t] = lds64(hx ? ot + 8 : ot);
+          S[t] = lds64(A[(10 + u - 2 * t) & (NRING - 1)] + hx * HALF);
+          N[t] = lds64(A[(12 + u - 2 * t) & (NRING - 1)] + hx * HALF);
+          O[t] = lds64(me);
+          F[t] = lds64(me + SRC);
         }
         // ---- 2S independent updates
 #pragma unroll
@@ -128,22 +156,31 @@ __device__ __forceinline__ void sweep_warp_body(const SweepArgs &a, double *ring
 #pragma unroll
         for (int t = 0; t < NST; ++t) {
           const int hx = (t + u + P0) & 1;
-          const int slot = (u - 2 * t) & (NRING - 1);
-          if (on[t]) rp[(slot * 2 + hx) * 32] = V[t];
+          const bool on = ((unsigned)(qi - 2 * t - 1) <= q_hi) && (hx ? upd_o : upd_e);
+          if (on) sts64(A[(11 + u - 2 * t) & (NRING - 1)] + hx * HALF, V[t]);
         }
-        load_row(qi + PF, (u + PF) & (NRING - 1));
+        load_row(qi + PF < nrows, A[(11 + u + PF) & (NRING - 1)], pin, psr);
+        pin += rowb;
+        psr += rowb;
         cp_async_wait<PF - 2>();  // row qi+2 has landed (stage 0 of the next step reads it)
         __syncwarp();
-        // ---- row w is final once the last pass has processed it: write the tile interior back
-        const int w = zl + qi - 2 * (NST - 1);
-        if (w >= z0 && w < z1) {
-          const int slot = (u - 2 * (NST - 1)) & (NRING - 1);
-          double *orow = gout + (size_t)w * nr + cl;
-          if (wr_e) orow[xe] = rp[(slot * 2) * 32];
-          if (wr_o) orow[xo] = rp[(slot * 2 + 1) * 32];
+        // ---- relative row qi - 2(NST-1) is final once the last pass has processed it: write the tile interior back
+        if ((unsigned)qi - w_lo < w_n) {
+          const unsigned sa = A[(11 + u - 2 * (NST - 1)) & (NRING - 1)];
+          if (wr_e) *(double *)pout = lds64(sa);
+          if (wr_o) *(double *)(pout + 8) = lds64(sa + HALF);
         }
+        pout += rowb;
       }
     }
+    // the ring moves on by UNR rows
+    unsigned head[UNR];
+#pragma unroll
+    for (int i = 0; i < UNR; ++i) head[i] = A[i];
+#pragma unroll
+    for (int i = 0; i + UNR < NRING; ++i) A[i] = A[i + UNR];
+#pragma unroll
+    for (int i = 0; i < UNR; ++i) A[NRING - UNR + i] = head[i];
   }
   // rows that no stage ever processes (next to the array edge: walls / halo rows)
   if (gout != gin) {
@@ -157,14 +194,15 @@ __device__ __forceinline__ void sweep_warp_body(const SweepArgs &a, double *ring
   }
 }
 
-template <int NST>
+template <int NST, int UNR>
 __global__ void __launch_bounds__(32 * kSwWPC) k_sweep_warp(const SweepArgs a) {
   constexpr int NRING = 16;
   constexpr int STEP = kSwCols - 2 * NST;  // interior columns per strip (even)
   extern __shared__ double sw_pool[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  double *ring_p = sw_pool + 8 + wid * (2 * NRING * kSwCols);  // [NRING][2][32]; +8: lane 0 may read element -1
-  double *ring_s = ring_p + NRING * kSwCols;                   // [NRING][2][32]
+  // per warp: psi ring [NRING][2][32] followed by the source ring [NRING][2][32].  (Edge lanes read one element
+  // outside their half row - the neighbouring half row of the same slot - and never use it.)
+  double *ring = sw_pool + wid * (2 * NRING * kSwCols);
   const int b = blockIdx.z;
   if (a.active && !a.active[b]) return;
   // (strip, band) tiles are numbered linearly and dealt four to a CTA, so CTAs are full whatever the strip count
@@ -183,15 +221,15 @@ __global__ void __launch_bounds__(32 * kSwWPC) k_sweep_warp(const SweepArgs a) {
   const double *gsrc = a.src + (size_t)b * a.sstride;
   double *gout = a.out + (size_t)b * a.ostride;
   if ((zl + a.par_off + cl) & 1)
-    sweep_warp_body<NST, 1>(a, ring_p, ring_s, lane, zl, zh, z0, z1, cl, wb, c0, c1, gin, gsrc, gout);
+    sweep_warp_body<NST, 1, UNR>(a, ring, lane, zl, zh, z0, z1, cl, wb, c0, c1, gin, gsrc, gout);
   else
-    sweep_warp_body<NST, 0>(a, ring_p, ring_s, lane, zl, zh, z0, z1, cl, wb, c0, c1, gin, gsrc, gout);
+    sweep_warp_body<NST, 0, UNR>(a, ring, lane, zl, zh, z0, z1, cl, wb, c0, c1, gin, gsrc, gout);
 }
 
 static size_t sweep_smem_bytes(int nst) {
   const int nring = 16;
   (void)nst;
-  return (size_t)(kSwWPC * 2 * nring * kSwCols + 8) * sizeof(double);
+  return (size_t)(kSwWPC * 2 * nring * kSwCols) * sizeof(double);
 }
 
 // Tile plan: strips of (64 - 2*NST) interior columns (one strip when the row fits 64 columns); row
@@ -253,15 +291,29 @@ int sweep_fused_launch(const LevelGeom &g, const double *in, size_t istride, dou
   a.active = active;
   const size_t smem = sweep_smem_bytes(nst);
   const dim3 grd((ns * nb + kSwWPC - 1) / kSwWPC, 1, batch), blk(32 * kSwWPC, 1, 1);
-  GSB_SMEM_OPT_IN(k_sweep_warp<2>, sweep_smem_bytes(2));
-  GSB_SMEM_OPT_IN(k_sweep_warp<4>, sweep_smem_bytes(4));
-  GSB_SMEM_OPT_IN(k_sweep_warp<6>, sweep_smem_bytes(6));
+  static const int unroll = [] {  // measurement switch: steps per loop body (2 or 4)
+    const char *e = std::getenv("GSB_SWEEP_UNROLL");
+    const int v = e ? std::atoi(e) : 2;
+    return (v == 2 || v == 4) ? v : 2;
+  }();
+#define GSB_SWEEP_LAUNCH(NST_, UNR_)                                   \
+  do {                                                                 \
+    GSB_SMEM_OPT_IN((k_sweep_warp<NST_, UNR_>), smem);                 \
+    k_sweep_warp<NST_, UNR_><<<grd, blk, smem, st>>>(a);               \
+  } while (0)
+#define GSB_SWEEP_DISPATCH(NST_)                                       \
+  do {                                                                 \
+    if (unroll == 4) GSB_SWEEP_LAUNCH(NST_, 4);                        \
+    else GSB_SWEEP_LAUNCH(NST_, 2);                                    \
+  } while (0)
   if (nst == 2)
-    k_sweep_warp<2><<<grd, blk, smem, st>>>(a);
+    GSB_SWEEP_DISPATCH(2);
   else if (nst == 4)
-    k_sweep_warp<4><<<grd, blk, smem, st>>>(a);
+    GSB_SWEEP_DISPATCH(4);
   else
-    k_sweep_warp<6><<<grd, blk, smem, st>>>(a);
+    GSB_SWEEP_DISPATCH(6);
+#undef GSB_SWEEP_DISPATCH
+#undef GSB_SWEEP_LAUNCH
   GSB_LAUNCH_CHECK();
   return GSB_OK;
 }
