@@ -194,6 +194,169 @@ __device__ __forceinline__ void sweep_warp_body(const SweepArgs &a, double *ring
   }
 }
 
+// Register-carried variant (the "register blocking" of the smoother).  A lane owns the column pair (2k, 2k+1) of the
+// strip, and of the five neighbours of an update only ONE belongs to another lane (west of the even column / east of the
+// odd one); everything else the same lane produced itself a few steps earlier:
+//   stage t at step qi updates (row q = qi - 2t, half hx):   K_t(qi) := the point's value afterwards (V, or O if masked)
+//     N     = (q+1, hx)    = K_{t-1}(qi-1)        S = (q-1, hx) = K_{t-1}(qi-3)
+//     own W/E = (q, 1-hx)  = K_{t-1}(qi-2)        O = (q, hx)   = K_{t-2}(qi-4)      F = source(q, hx) = F_{t-2}(qi-4)
+//   stage 0 reads fresh input: a(qi) = in(qi+1, hx) and b(qi) = in(qi, hx) cover every input point exactly once, and
+//     its own W/E = a(qi-1), S = a(qi-2);  stage 1's O = a(qi-3).
+// With the step loop unrolled by 4 every carried value has a fixed register name (index = step & 3), so the ring in
+// shared memory is only the landing zone of the asynchronous row copies and the mailbox for the one neighbour value:
+// 10 shared loads + 5 stores per step instead of 42 + 6 (the r2 kernel ran the shared-memory pipe at 74 %,
+// profiles/r2_sweep_icache.md), and finished rows go from registers straight to global memory.
+// The arithmetic and its order are those of the ring kernel: results are bit-identical.
+template <int NST, int P0>
+__device__ __forceinline__ void sweep_warp_body_rc(const SweepArgs &a, double *ring, int lane, int zl,
+                                                   int zh, int z0, int z1, int cl, int wb, int c0, int c1,
+                                                   const double *gin, const double *gsrc, double *gout) {
+  constexpr int NRING = 16;
+  constexpr int PF = NRING - 2 * NST;
+  constexpr int UNR = 4;
+  constexpr int L = NST - 1;  // last stage
+  constexpr unsigned SLOT = 64 * 8, HALF = 32 * 8, SRC = NRING * SLOT;
+  const int nr = a.nr;
+  const int xe = 2 * lane, xo = 2 * lane + 1;
+  const bool have_e = xe < wb, have_o = xo < wb;
+  const bool upd_e = xe >= 1 && xe <= wb - 2, upd_o = xo <= wb - 2;
+  const bool wr_e = have_e && cl + xe >= c0 && cl + xe < c1, wr_o = have_o && cl + xo >= c0 && cl + xo < c1;
+  const double ae_e = have_e ? a.a_e[cl + xe] : 0.0, aw_e = have_e ? a.a_w[cl + xe] : 0.0;
+  const double ae_o = have_o ? a.a_e[cl + xo] : 0.0, aw_o = have_o ? a.a_w[cl + xo] : 0.0;
+  const double a_ns = a.a_ns, a_c = a.a_c, inv_a_c = a.inv_a_c, omega = a.omega, omw = a.omw;
+  const unsigned rb = (unsigned)__cvta_generic_to_shared(ring) + (unsigned)lane * 8u;
+  const int nrows = zh - zl;
+  const size_t rowb = (size_t)nr * sizeof(double);
+
+  auto load_row = [&](bool row_ok, unsigned sa, const char *pr, const char *sr) {
+    if (row_ok) {
+      if (have_e) {
+        cp_async8s(sa, pr);
+        cp_async8s(sa + SRC, sr);
+      }
+      if (have_o) {
+        cp_async8s(sa + HALF, pr + 8);
+        cp_async8s(sa + SRC + HALF, sr + 8);
+      }
+    }
+    cp_async_commit();
+  };
+  const char *pin = (const char *)(gin + (size_t)zl * nr + cl + xe);
+  const char *psr = (const char *)(gsrc + (size_t)zl * nr + cl + xe);
+#pragma unroll
+  for (int q = 0; q < PF; ++q) load_row(q < nrows, rb + q * SLOT, pin + q * rowb, psr + q * rowb);
+  pin += (size_t)PF * rowb;  // the row step qi = 0 prefetches
+  psr += (size_t)PF * rowb;
+  cp_async_wait<PF - 2>();  // rows 0 and 1 have landed
+  __syncwarp();
+
+  unsigned A[NRING];  // A[i]: slot of relative row base - 11 + i
+#pragma unroll
+  for (int i = 0; i < NRING; ++i) A[i] = rb + ((i + 5) & (NRING - 1)) * SLOT;
+  char *pout = (char *)(gout + cl + xe) + ((ptrdiff_t)zl - 2 * L) * (ptrdiff_t)rowb;  // row written at step 0
+  const unsigned w_lo = (unsigned)(z0 - zl + 2 * L), w_n = (unsigned)(z1 - z0);
+  const unsigned q_hi = (unsigned)(nrows - 3);
+  const int q_end = (nrows - 1) + 2 * L;  // the last loaded row leaves the last stage at this step
+  double K[NST][UNR], Fc[NST][UNR], A4[UNR];
+#pragma unroll
+  for (int t = 0; t < NST; ++t)
+#pragma unroll
+    for (int i = 0; i < UNR; ++i) K[t][i] = Fc[t][i] = 0.0;
+#pragma unroll
+  for (int i = 0; i < UNR; ++i) A4[i] = 0.0;
+  // a(-1) = in(0, 1 - P0): the half of row 0 that no step loads (a(qi) covers rows >= 1, b(0) the other half of row 0)
+  A4[UNR - 1] = lds64(rb + (1 - P0) * HALF);
+
+  for (int base = 0; base <= q_end; base += UNR) {
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int qi = base + u;
+      if (qi <= q_end) {
+        constexpr int M = UNR - 1;
+        double Wv[NST], Ev[NST], Sv[NST], Nv[NST], Ov[NST], Fv[NST], own[NST];
+        // ---- shared-memory reads: the neighbour lane's value for every stage, fresh input for stage 0, sources
+#pragma unroll
+        for (int t = 0; t < NST; ++t) {
+          const int hx = (t + u + P0) & 1;
+          const unsigned row = A[(11 + u - 2 * t) & (NRING - 1)];
+          const double nb = lds64(hx ? row + 8 : row + HALF - 8);  // east of the odd column / west of the even one
+          if (t == 0) {
+            Ov[0] = lds64(row + hx * HALF);                                        // b(qi)
+            Nv[0] = lds64(A[(12 + u) & (NRING - 1)] + hx * HALF);                  // a(qi)
+            own[0] = A4[(u - 1) & M];
+            Sv[0] = A4[(u - 2) & M];
+            Fv[0] = lds64(row + hx * HALF + SRC);
+          } else {
+            Nv[t] = K[t - 1][(u - 1) & M];
+            own[t] = K[t - 1][(u - 2) & M];
+            Sv[t] = K[t - 1][(u - 3) & M];
+            if (t == 1) {
+              Ov[1] = A4[(u - 3) & M];
+              Fv[1] = lds64(row + hx * HALF + SRC);
+            } else {
+              Ov[t] = K[t - 2][u & M];
+              Fv[t] = Fc[t - 2][u & M];
+            }
+          }
+          Wv[t] = hx ? own[t] : nb;
+          Ev[t] = hx ? nb : own[t];
+        }
+        A4[u & M] = Nv[0];
+        // ---- 2S independent updates
+        double Kn[NST];
+#pragma unroll
+        for (int t = 0; t < NST; ++t) {
+          const int hx = (t + u + P0) & 1;
+          double acc = dadd(dmul(hx ? ae_o : ae_e, Ev[t]), dmul(hx ? aw_o : aw_e, Wv[t]));
+          acc = dadd(acc, dmul(a_ns, Sv[t]));
+          acc = dadd(acc, dmul(a_ns, Nv[t]));
+          acc = dsub(acc, Fv[t]);
+          const double qq = __dmul_rn(acc, inv_a_c);
+          const double gs = __fma_rn(__fma_rn(-a_c, qq, acc), inv_a_c, qq);  // acc / a_c (Markstein sequence, gsb_internal.cuh)
+          const double V = dadd(dmul(omw, Ov[t]), dmul(omega, gs));
+          const bool on = ((unsigned)(qi - 2 * t - 1) <= q_hi) && (hx ? upd_o : upd_e);
+          Kn[t] = on ? V : Ov[t];
+          if (t < L && on) sts64(A[(11 + u - 2 * t) & (NRING - 1)] + hx * HALF, V);  // mailbox for the neighbour lane
+        }
+#pragma unroll
+        for (int t = 0; t < NST; ++t) {
+          K[t][u & M] = Kn[t];
+          Fc[t][u & M] = Fv[t];
+        }
+        load_row(qi + PF < nrows, A[(11 + u + PF) & (NRING - 1)], pin, psr);
+        pin += rowb;
+        psr += rowb;
+        cp_async_wait<PF - 2>();  // row qi+2 has landed (stage 0 of the next step reads it)
+        __syncwarp();
+        // ---- relative row qi - 2L is final: both halves are in registers
+        if ((unsigned)qi - w_lo < w_n) {
+          const int hxl = (L + u + P0) & 1;
+          const double ve = hxl ? own[L] : Kn[L], vo = hxl ? Kn[L] : own[L];
+          if (wr_e) *(double *)pout = ve;
+          if (wr_o) *(double *)(pout + 8) = vo;
+        }
+        pout += rowb;
+      }
+    }
+    unsigned hd[UNR];
+#pragma unroll
+    for (int i = 0; i < UNR; ++i) hd[i] = A[i];
+#pragma unroll
+    for (int i = 0; i + UNR < NRING; ++i) A[i] = A[i + UNR];
+#pragma unroll
+    for (int i = 0; i < UNR; ++i) A[NRING - UNR + i] = hd[i];
+  }
+  if (gout != gin) {
+    for (int w = z0; w < z1; ++w) {
+      if (w >= zl + 1 && w <= zh - 2) continue;
+      const double *irow = gin + (size_t)w * nr + cl;
+      double *orow = gout + (size_t)w * nr + cl;
+      if (wr_e) orow[xe] = irow[xe];
+      if (wr_o) orow[xo] = irow[xo];
+    }
+  }
+}
+
 template <int NST, int UNR>
 __global__ void __launch_bounds__(32 * kSwWPC) k_sweep_warp(const SweepArgs a) {
   constexpr int NRING = 16;
@@ -220,10 +383,17 @@ __global__ void __launch_bounds__(32 * kSwWPC) k_sweep_warp(const SweepArgs a) {
   const double *gin = a.in + (size_t)b * a.istride;
   const double *gsrc = a.src + (size_t)b * a.sstride;
   double *gout = a.out + (size_t)b * a.ostride;
-  if ((zl + a.par_off + cl) & 1)
-    sweep_warp_body<NST, 1, UNR>(a, ring, lane, zl, zh, z0, z1, cl, wb, c0, c1, gin, gsrc, gout);
-  else
-    sweep_warp_body<NST, 0, UNR>(a, ring, lane, zl, zh, z0, z1, cl, wb, c0, c1, gin, gsrc, gout);
+  if constexpr (UNR == 1) {  // register-carried variant
+    if ((zl + a.par_off + cl) & 1)
+      sweep_warp_body_rc<NST, 1>(a, ring, lane, zl, zh, z0, z1, cl, wb, c0, c1, gin, gsrc, gout);
+    else
+      sweep_warp_body_rc<NST, 0>(a, ring, lane, zl, zh, z0, z1, cl, wb, c0, c1, gin, gsrc, gout);
+  } else {
+    if ((zl + a.par_off + cl) & 1)
+      sweep_warp_body<NST, 1, UNR>(a, ring, lane, zl, zh, z0, z1, cl, wb, c0, c1, gin, gsrc, gout);
+    else
+      sweep_warp_body<NST, 0, UNR>(a, ring, lane, zl, zh, z0, z1, cl, wb, c0, c1, gin, gsrc, gout);
+  }
 }
 
 static size_t sweep_smem_bytes(int nst) {
@@ -291,10 +461,10 @@ int sweep_fused_launch(const LevelGeom &g, const double *in, size_t istride, dou
   a.active = active;
   const size_t smem = sweep_smem_bytes(nst);
   const dim3 grd((ns * nb + kSwWPC - 1) / kSwWPC, 1, batch), blk(32 * kSwWPC, 1, 1);
-  static const int unroll = [] {  // measurement switch: steps per loop body (2 or 4)
+  static const int unroll = [] {  // measurement switch: ring kernel with 2 or 4 steps per loop body, 1 = register-carried
     const char *e = std::getenv("GSB_SWEEP_UNROLL");
     const int v = e ? std::atoi(e) : 2;
-    return (v == 2 || v == 4) ? v : 2;
+    return (v == 1 || v == 2 || v == 4) ? v : 2;
   }();
 #define GSB_SWEEP_LAUNCH(NST_, UNR_)                                   \
   do {                                                                 \
@@ -304,6 +474,7 @@ int sweep_fused_launch(const LevelGeom &g, const double *in, size_t istride, dou
 #define GSB_SWEEP_DISPATCH(NST_)                                       \
   do {                                                                 \
     if (unroll == 4) GSB_SWEEP_LAUNCH(NST_, 4);                        \
+    else if (unroll == 1) GSB_SWEEP_LAUNCH(NST_, 1);                   \
     else GSB_SWEEP_LAUNCH(NST_, 2);                                    \
   } while (0)
   if (nst == 2)
