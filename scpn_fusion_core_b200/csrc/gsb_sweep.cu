@@ -53,6 +53,9 @@ __device__ __forceinline__ double lds64(unsigned a) {
   return v;
 }
 __device__ __forceinline__ void sts64(unsigned a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v)); }
+__device__ __forceinline__ void sts64_if(bool p, unsigned a, double v) {  // predicated store, no branch
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p st.shared.f64 [%0], %1;\n\t}" ::"r"(a), "d"(v), "r"((int)p));
+}
 __device__ __forceinline__ void cp_async8s(unsigned s, const void *gmem) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem) : "memory");
 }
@@ -305,7 +308,7 @@ __device__ __forceinline__ void sweep_warp_body_rc(const SweepArgs &a, double *r
         // ---- 2S independent updates
         double Kn[NST];
 #pragma unroll
-        for (int t = 0; t < NST; ++t) {
+        for (int t = NST - 1; t >= 0; --t) {  // last stage first: stage t+2 has consumed K[t][u] before stage t renews it
           const int hx = (t + u + P0) & 1;
           double acc = dadd(dmul(hx ? ae_o : ae_e, Ev[t]), dmul(hx ? aw_o : aw_e, Wv[t]));
           acc = dadd(acc, dmul(a_ns, Sv[t]));
@@ -316,7 +319,7 @@ __device__ __forceinline__ void sweep_warp_body_rc(const SweepArgs &a, double *r
           const double V = dadd(dmul(omw, Ov[t]), dmul(omega, gs));
           const bool on = ((unsigned)(qi - 2 * t - 1) <= q_hi) && (hx ? upd_o : upd_e);
           Kn[t] = on ? V : Ov[t];
-          if (t < L && on) sts64(A[(11 + u - 2 * t) & (NRING - 1)] + hx * HALF, V);  // mailbox for the neighbour lane
+          if (t < L) sts64_if(on, A[(11 + u - 2 * t) & (NRING - 1)] + hx * HALF, V);  // mailbox for the neighbour lane
         }
 #pragma unroll
         for (int t = 0; t < NST; ++t) {
@@ -461,10 +464,10 @@ int sweep_fused_launch(const LevelGeom &g, const double *in, size_t istride, dou
   a.active = active;
   const size_t smem = sweep_smem_bytes(nst);
   const dim3 grd((ns * nb + kSwWPC - 1) / kSwWPC, 1, batch), blk(32 * kSwWPC, 1, 1);
-  static const int unroll = [] {  // measurement switch: ring kernel with 2 or 4 steps per loop body, 1 = register-carried
+  static const int unroll = [] {  // 1 (default) = register-carried kernel; measurement switch: 2 / 4 = ring kernel with that many steps per loop body
     const char *e = std::getenv("GSB_SWEEP_UNROLL");
-    const int v = e ? std::atoi(e) : 2;
-    return (v == 1 || v == 2 || v == 4) ? v : 2;
+    const int v = e ? std::atoi(e) : 1;
+    return (v == 1 || v == 2 || v == 4) ? v : 1;
   }();
 #define GSB_SWEEP_LAUNCH(NST_, UNR_)                                   \
   do {                                                                 \
