@@ -111,6 +111,11 @@ int gsb_smooth_ex(gsb_ctx *ctx, double *psi_dev, const double *src_dev, int batc
 /* a3: out-of-place toroidal Jacobi step with sanitise+clip (_jacobi_step, :54-95). */
 int gsb_jacobi(gsb_ctx *ctx, const double *psi_dev, const double *src_dev, double *out_dev,
                int batch, void *stream);
+/* a3 repeated: n_steps Jacobi steps in place (result in psi_dev; tmp_dev [batch][nz][nr] is scratch) - the Picard
+ * seed's 50 steps (_seed_plasma, fusion_kernel_iterative_solver.py:410-415).  Groups of 5 steps run in one pass over
+ * HBM (temporally blocked, register-carried kernel); results are bit-identical to n_steps calls of gsb_jacobi. */
+int gsb_jacobi_steps(gsb_ctx *ctx, double *psi_dev, const double *src_dev, double *tmp_dev, int n_steps,
+                     int batch, void *stream);
 /* a4: r = L*psi - src on the interior, 0 on the wall (mg_residual, :211-249). */
 int gsb_residual(gsb_ctx *ctx, const double *psi_dev, const double *src_dev, double *res_dev,
                  int batch, void *stream);

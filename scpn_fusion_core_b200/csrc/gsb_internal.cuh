@@ -384,6 +384,11 @@ int residual_restrict_tiled_launch(const LevelGeom &g, const double *psi, size_t
                                    size_t sstride, double *dc, size_t dstride, int nzc, int nrc, int roff, int ci0,
                                    int ci1, int zero_rest, int split_out, int batch, const int *active,
                                    cudaStream_t st);
+constexpr int kJacobiFused = 5;  // Jacobi steps per pass of the temporally blocked kernel (gsb_sweep.cu)
+int jacobi_fused_launch(const LevelGeom &g, const double *in, double *out, const double *src, int batch, int num_sms,
+                        const int *active, cudaStream_t st);
+int jacobi_steps_launch(gsb_ctx *ctx, double *psi, double *tmp, const double *src, int n_steps, int batch,
+                        const int *active, cudaStream_t st);
 int jacobi_launch(const LevelGeom &g, const double *psi, const double *src, double *out, int batch,
                   const int *active, cudaStream_t st);
 int ring_save_launch(const double *f, size_t stride, double *ring, int nz, int nr, int batch,

@@ -112,6 +112,14 @@ k_jacobi(LevelGeom g, const double *__restrict__ psi, const double *__restrict__
   out[b * n + (size_t)iz * g.nr + ir] = v;
 }
 
+__global__ void __launch_bounds__(256)
+k_copy_masked(const double *__restrict__ src, double *__restrict__ dst, size_t n, const int *__restrict__ active) {
+  const int b = blockIdx.y;
+  if (!active[b]) return;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    dst[(size_t)b * n + i] = src[(size_t)b * n + i];
+}
+
 int jacobi_launch(const LevelGeom &g, const double *psi, const double *src, double *out, int batch,
                   const int *active, cudaStream_t st) {
   const dim3 blk(32, 8, 1);
@@ -120,6 +128,41 @@ int jacobi_launch(const LevelGeom &g, const double *psi, const double *src, doub
   GSB_LAUNCH_CHECK();
   return GSB_OK;
 }
+
+// n_steps Jacobi steps, result in psi_dev; tmp_dev is the ping-pong partner.  Groups of kJacobiFused steps run in
+// one pass over HBM (k_jacobi_warp), the rest one step per launch.
+int jacobi_steps_launch(gsb_ctx *ctx, double *psi, double *tmp, const double *src, int n_steps, int batch,
+                        const int *active, cudaStream_t st) {
+  const LevelGeom &g = ctx->levels[0].g;
+  const size_t bytes = (size_t)batch * ctx->n * sizeof(double);
+  double *cur = psi, *oth = tmp;
+  const bool fused_ok = g.nz >= 3 && g.nr >= 3 && !std::getenv("GSB_NO_FUSED_JACOBI");
+  int left = n_steps;
+  while (left > 0) {
+    int rc;
+    if (fused_ok && left >= kJacobiFused) {
+      rc = jacobi_fused_launch(g, cur, oth, src, batch, ctx->num_sms, active, st);
+      left -= kJacobiFused;
+    } else {
+      rc = jacobi_launch(g, cur, src, oth, batch, active, st);
+      left -= 1;
+    }
+    if (rc) return rc;
+    std::swap(cur, oth);
+  }
+  if (cur != psi) {
+    // inactive equilibria were never written in `tmp`: copy only through a kernel that honours the mask
+    if (active) {
+      const int blocks = (int)std::min<size_t>((ctx->n + 255) / 256, 64);
+      k_copy_masked<<<dim3(blocks, batch), 256, 0, st>>>(cur, psi, ctx->n, active);
+      GSB_LAUNCH_CHECK();
+    } else {
+      GSB_CUDA(cudaMemcpyAsync(psi, cur, bytes, cudaMemcpyDeviceToDevice, st));
+    }
+  }
+  return GSB_OK;
+}
+
 
 // ------------------------------------------------------------------------------------------
 // a4  residual / operator  (multigrid_solve.py:236-249)
@@ -812,6 +855,17 @@ int gsb_jacobi(gsb_ctx *ctx, const double *psi_dev, const double *src_dev, doubl
   int rc = ensure_plan(ctx, ctx->planned_min_grid < 0 ? 5 : ctx->planned_min_grid);
   if (rc) return rc;
   return jacobi_launch(ctx->levels[0].g, psi_dev, src_dev, out_dev, batch, nullptr, (cudaStream_t)stream);
+}
+
+int gsb_jacobi_steps(gsb_ctx *ctx, double *psi_dev, const double *src_dev, double *tmp_dev, int n_steps, int batch,
+                     void *stream) {
+  GSB_REQUIRE(ctx && psi_dev && src_dev && tmp_dev, "gsb_jacobi_steps: NULL argument");
+  GSB_REQUIRE(batch >= 1 && batch <= ctx->batch_cap, "gsb_jacobi_steps: batch outside [1, batch_cap]");
+  GSB_REQUIRE(n_steps >= 0, "gsb_jacobi_steps: n_steps must be >= 0");
+  GSB_CUDA(cudaSetDevice(ctx->device));
+  int rc = ensure_plan(ctx, ctx->planned_min_grid < 0 ? 5 : ctx->planned_min_grid);
+  if (rc) return rc;
+  return jacobi_steps_launch(ctx, psi_dev, tmp_dev, src_dev, n_steps, batch, nullptr, (cudaStream_t)stream);
 }
 
 static int residual_common(gsb_ctx *ctx, const double *psi, const double *src, double *out, int batch,

@@ -2275,12 +2275,9 @@ static int picard_solve_impl(gsb_ctx *ctx, const gsb_picard_params *p, double *p
     volatile double ssum2 = ssum * ctx->dz;
     k_seed_source<<<dim3(copy_blocks, batch), 256, 0, st>>>(n, nr, w->seedJ, ssum2, ip_dev, w->mr, jphi_dev, w->source, s.seed_active);
     GSB_LAUNCH_CHECK();
-    for (int it = 0; it < 25; ++it) {  // 50 Jacobi steps, ping-pong psi <-> W
-      rc = jacobi_launch(g, psi_dev, w->source, w->W, batch, s.seed_active, st);
-      if (rc) return rc;
-      rc = jacobi_launch(g, w->W, w->source, psi_dev, batch, s.seed_active, st);
-      if (rc) return rc;
-    }
+    // 50 Jacobi steps, ping-pong psi <-> W (five steps per pass over HBM, gsb_sweep.cu: k_jacobi_warp)
+    rc = jacobi_steps_launch(ctx, psi_dev, w->W, w->source, 50, batch, s.seed_active, st);
+    if (rc) return rc;
   }
 
   AndersonBufs mixb{};

@@ -399,6 +399,212 @@ __global__ void __launch_bounds__(32 * kSwWPC) k_sweep_warp(const SweepArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Temporally blocked Jacobi: T steps of _jacobi_step (fusion_kernel_iterative_solver.py:54-95; sanitised inputs, clipped
+// output, walls = sanitised copy) in ONE pass over HBM, register-carried like sweep_warp_body_rc.  The Picard seed is 50
+// of these steps per solve; one step per launch (k_jacobi) moved 24 B per point per step at 1.25 TB/s.
+//   stage t at step qi produces level t+1 of row q = qi - 2t, both of the lane's columns:
+//     N = K_{t-1}(qi-1), C = K_{t-1}(qi-2) (the row itself: O of a masked point, E of the even / W of the odd column),
+//     S = K_{t-1}(qi-3), source = F_{t-1}(qi-2); west of the even column / east of the odd one come from the neighbour
+//     lanes through the shared-memory ring (mailbox), which stage t then overwrites with its own level.
+//   Carried values of the inner stages are kept SANITISED (what the next step's _sanitize_numeric_array makes of them);
+//   the last stage writes its raw result (np.clip propagates NaN).
+// Branch-free forms of sanitize / clip_cap (gsb_internal.cuh): same results, no slow-path code in the unrolled body.
+__device__ __forceinline__ double sanitize_bf(double v) {  // NaN -> 0, +-inf and out-of-range -> +-cap
+  const double r = (fabs(v) <= kCap) ? v : copysign(kCap, v);
+  return (v != v) ? 0.0 : r;
+}
+__device__ __forceinline__ double clip_cap_bf(double v) {  // np.clip: NaN stays NaN
+  return (fabs(v) <= kCap || v != v) ? v : copysign(kCap, v);
+}
+
+template <int T>
+__device__ __forceinline__ void jacobi_warp_body(const SweepArgs &a, double *ring, int lane, int zl, int zh, int z0,
+                                                 int z1, int cl, int wb, int c0, int c1, const double *gin,
+                                                 const double *gsrc, double *gout) {
+  constexpr int NRING = 16;
+  constexpr int PF = 5;  // rows qi-2(T-1) .. qi+PF live: 2T-1+PF <= 16
+  static_assert(2 * T - 1 + PF <= NRING && T >= 1, "ring too small");
+  constexpr int UNR = 4, M = UNR - 1;
+  constexpr int L = T - 1;
+  constexpr unsigned SLOT = 64 * 8, HALF = 32 * 8, SRC = NRING * SLOT;
+  const int nr = a.nr;
+  const int xe = 2 * lane, xo = 2 * lane + 1;
+  const bool have_e = xe < wb, have_o = xo < wb;
+  const bool upd_e = xe >= 1 && xe <= wb - 2, upd_o = xo <= wb - 2;
+  const bool wr_e = have_e && cl + xe >= c0 && cl + xe < c1, wr_o = have_o && cl + xo >= c0 && cl + xo < c1;
+  const double ae_e = have_e ? a.a_e[cl + xe] : 0.0, aw_e = have_e ? a.a_w[cl + xe] : 0.0;
+  const double ae_o = have_o ? a.a_e[cl + xo] : 0.0, aw_o = have_o ? a.a_w[cl + xo] : 0.0;
+  const double a_ns = a.a_ns, a_c = a.a_c, inv_a_c = a.inv_a_c;
+  const unsigned rb = (unsigned)__cvta_generic_to_shared(ring) + (unsigned)lane * 8u;
+  const int nrows = zh - zl;
+  const size_t rowb = (size_t)nr * sizeof(double);
+
+  auto load_row = [&](bool row_ok, unsigned sa, const char *pr, const char *sr) {
+    if (row_ok) {
+      if (have_e) {
+        cp_async8s(sa, pr);
+        cp_async8s(sa + SRC, sr);
+      }
+      if (have_o) {
+        cp_async8s(sa + HALF, pr + 8);
+        cp_async8s(sa + SRC + HALF, sr + 8);
+      }
+    }
+    cp_async_commit();
+  };
+  const char *pin = (const char *)(gin + (size_t)zl * nr + cl + xe);
+  const char *psr = (const char *)(gsrc + (size_t)zl * nr + cl + xe);
+#pragma unroll
+  for (int q = 0; q < PF; ++q) load_row(q < nrows, rb + q * SLOT, pin + q * rowb, psr + q * rowb);
+  pin += (size_t)PF * rowb;
+  psr += (size_t)PF * rowb;
+  cp_async_wait<PF - 2>();  // rows 0 and 1 have landed
+  __syncwarp();
+
+  unsigned A[NRING];  // A[i]: slot of relative row base - 11 + i
+#pragma unroll
+  for (int i = 0; i < NRING; ++i) A[i] = rb + ((i + 5) & (NRING - 1)) * SLOT;
+  char *pout = (char *)(gout + cl + xe) + ((ptrdiff_t)zl - 2 * L) * (ptrdiff_t)rowb;  // row written at step 0
+  const unsigned w_lo = (unsigned)(z0 - zl + 2 * L), w_n = (unsigned)(z1 - z0);
+  const unsigned q_hi = (unsigned)(nrows - 3);
+  const int q_end = (nrows - 1) + 2 * L;
+  // level-t values of the lane's two columns for the last four rows stage t handled, and their sources
+  // (the last stage's values are not carried: nothing consumes them; sources are consumed two steps later only)
+  constexpr int TC = T > 1 ? T - 1 : 1;
+  double Ke[TC][UNR], Ko[TC][UNR], Fe[TC][2], Fo[TC][2], Ae[UNR], Ao[UNR];
+#pragma unroll
+  for (int t = 0; t < TC; ++t) {
+#pragma unroll
+    for (int i = 0; i < UNR; ++i) Ke[t][i] = Ko[t][i] = 0.0;
+    Fe[t][0] = Fe[t][1] = Fo[t][0] = Fo[t][1] = 0.0;
+  }
+#pragma unroll
+  for (int i = 0; i < UNR; ++i) Ae[i] = Ao[i] = 0.0;
+  Ae[UNR - 1] = sanitize_bf(lds64(rb));  // a(-1) = in(0, .): stage 0 sees row 0 as "the row itself" at step 0
+  Ao[UNR - 1] = sanitize_bf(lds64(rb + HALF));
+
+  for (int base = 0; base <= q_end; base += UNR) {
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int qi = base + u;
+      if (qi <= q_end) {
+        double nbW[T], nbE[T];
+        // ---- shared-memory reads: neighbour lanes' values of every stage's row, fresh input row qi+1, source row qi
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+          const unsigned row = A[(11 + u - 2 * t) & (NRING - 1)];
+          nbW[t] = lds64(row + HALF - 8);  // lane-1's odd column
+          nbE[t] = lds64(row + 8);         // lane+1's even column
+        }
+        nbW[0] = sanitize_bf(nbW[0]);  // stage 0 reads raw input; the mailbox values of later stages are sanitised
+        nbE[0] = sanitize_bf(nbE[0]);
+        const unsigned row0 = A[(11 + u) & (NRING - 1)], row1 = A[(12 + u) & (NRING - 1)];
+        const double a_e_new = sanitize_bf(lds64(row1)), a_o_new = sanitize_bf(lds64(row1 + HALF));
+        const double f_e_new = sanitize_bf(lds64(row0 + SRC)), f_o_new = sanitize_bf(lds64(row0 + SRC + HALF));
+        __syncwarp();  // every lane has read the mailbox rows before any lane overwrites them below
+        double Kne[T], Kno[T], Fne[T], Fno[T];
+#pragma unroll
+        for (int t = T - 1; t >= 0; --t) {
+          double Ce, Co, Se, So, Ne, No, fe, fo;
+          if (t == 0) {
+            Ne = a_e_new;
+            No = a_o_new;
+            Ce = Ae[(u - 1) & M];
+            Co = Ao[(u - 1) & M];
+            Se = Ae[(u - 2) & M];
+            So = Ao[(u - 2) & M];
+            fe = f_e_new;
+            fo = f_o_new;
+          } else {
+            Ne = Ke[t - 1][(u - 1) & M];
+            No = Ko[t - 1][(u - 1) & M];
+            Ce = Ke[t - 1][(u - 2) & M];
+            Co = Ko[t - 1][(u - 2) & M];
+            Se = Ke[t - 1][(u - 3) & M];
+            So = Ko[t - 1][(u - 3) & M];
+            fe = Fe[t - 1][u & 1];  // written two steps ago
+            fo = Fo[t - 1][u & 1];
+          }
+          // even column: E = own odd column, W = neighbour; odd column: W = own even column, E = neighbour
+          double acc = dadd(dmul(ae_e, Co), dmul(aw_e, nbW[t]));
+          acc = dadd(acc, dmul(a_ns, Se));
+          acc = dadd(acc, dmul(a_ns, Ne));
+          acc = dsub(acc, fe);
+          const double qe = ddiv_y(acc, a_c, inv_a_c);
+          acc = dadd(dmul(ae_o, nbE[t]), dmul(aw_o, Ce));
+          acc = dadd(acc, dmul(a_ns, So));
+          acc = dadd(acc, dmul(a_ns, No));
+          acc = dsub(acc, fo);
+          const double qo = ddiv_y(acc, a_c, inv_a_c);
+          const bool on_row = (unsigned)(qi - 2 * t - 1) <= q_hi;
+          // inner level: clip, then what the next step's sanitiser makes of it (= sanitize of the quotient); the last
+          // level keeps np.clip's NaN.  Masked points copy the (already sanitised) value of the level below.
+          const double ve = t < L ? sanitize_bf(qe) : clip_cap_bf(qe), vo = t < L ? sanitize_bf(qo) : clip_cap_bf(qo);
+          const double ke = (on_row && upd_e) ? ve : Ce, ko = (on_row && upd_o) ? vo : Co;
+          if (t < L) {  // mailbox for the neighbour lanes
+            const bool row_in = (unsigned)(qi - 2 * t) < (unsigned)nrows;
+            const unsigned row = A[(11 + u - 2 * t) & (NRING - 1)];
+            sts64_if(row_in && have_e, row, ke);
+            sts64_if(row_in && have_o, row + HALF, ko);
+          }
+          Kne[t] = ke;
+          Kno[t] = ko;
+          Fne[t] = fe;
+          Fno[t] = fo;
+        }
+#pragma unroll
+        for (int t = 0; t < L; ++t) {
+          Ke[t][u & M] = Kne[t];
+          Ko[t][u & M] = Kno[t];
+          Fe[t][u & 1] = Fne[t];
+          Fo[t][u & 1] = Fno[t];
+        }
+        Ae[u & M] = a_e_new;
+        Ao[u & M] = a_o_new;
+        load_row(qi + PF < nrows, A[(11 + u + PF) & (NRING - 1)], pin, psr);
+        pin += rowb;
+        psr += rowb;
+        cp_async_wait<PF - 2>();  // row qi+2 has landed (the next step reads it as its fresh row)
+        __syncwarp();
+        if ((unsigned)qi - w_lo < w_n) {  // relative row qi - 2L has passed the last stage
+          if (wr_e) *(double *)pout = Kne[L];
+          if (wr_o) *(double *)(pout + 8) = Kno[L];
+        }
+        pout += rowb;
+      }
+    }
+    unsigned hd[UNR];
+#pragma unroll
+    for (int i = 0; i < UNR; ++i) hd[i] = A[i];
+#pragma unroll
+    for (int i = 0; i + UNR < NRING; ++i) A[i] = A[i + UNR];
+#pragma unroll
+    for (int i = 0; i < UNR; ++i) A[NRING - UNR + i] = hd[i];
+  }
+}
+
+template <int T>
+__global__ void __launch_bounds__(32 * kSwWPC, 3) k_jacobi_warp(const SweepArgs a) {
+  constexpr int NRING = 16;
+  constexpr int STEP = kSwCols - 2 * T;  // interior columns per strip
+  extern __shared__ double sw_pool[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  double *ring = sw_pool + wid * (2 * NRING * kSwCols);
+  const int b = blockIdx.z;
+  if (a.active && !a.active[b]) return;
+  const int tile = blockIdx.x * kSwWPC + wid;
+  if (tile >= a.n_strips * a.n_bands) return;
+  const int band = tile / a.n_strips, strip = tile - band * a.n_strips;
+  const int nz = a.nz, nr = a.nr;
+  const int z0 = band * a.band_rows, z1 = min(nz, z0 + a.band_rows);
+  const int c0 = strip * STEP, c1 = (a.n_strips == 1) ? nr : min(nr, c0 + STEP);
+  const int zl = max(0, z0 - T), zh = min(nz, z1 + T);
+  const int cl = max(0, c0 - T), ch = min(nr, cl + kSwCols);
+  jacobi_warp_body<T>(a, ring, lane, zl, zh, z0, z1, cl, ch - cl, c0, c1, a.in + (size_t)b * a.istride,
+                      a.src + (size_t)b * a.sstride, a.out + (size_t)b * a.ostride);
+}
+
 static size_t sweep_smem_bytes(int nst) {
   const int nring = 16;
   (void)nst;
@@ -488,6 +694,49 @@ int sweep_fused_launch(const LevelGeom &g, const double *in, size_t istride, dou
     GSB_SWEEP_DISPATCH(6);
 #undef GSB_SWEEP_DISPATCH
 #undef GSB_SWEEP_LAUNCH
+  GSB_LAUNCH_CHECK();
+  return GSB_OK;
+}
+
+// T = 5 Jacobi steps per pass over HBM, out of place (in != out).
+int jacobi_fused_launch(const LevelGeom &g, const double *in, double *out, const double *src, int batch, int num_sms,
+                        const int *active, cudaStream_t st) {
+  constexpr int T = kJacobiFused;
+  GSB_REQUIRE(in != out, "jacobi_fused_launch: out of place only");
+  if (batch <= 0) return GSB_OK;
+  SweepArgs a{};
+  a.nz = g.nz;
+  a.nr = g.nr;
+  int ns, nb, sc;
+  // strips of 64 - 2T interior columns; bands as for the sweeps (T halo rows per side)
+  const int step = kSwCols - 2 * T;
+  if (g.nr <= kSwCols) {
+    ns = 1;
+  } else {
+    ns = (g.nr + step - 1) / step;
+  }
+  (void)sc;
+  const long long warps = (long long)ns * batch, want = 24LL * num_sms;
+  int bands = 1;
+  if (warps < want) bands = (int)std::min<long long>((want + warps - 1) / warps, std::max(1, g.nz / 8));
+  a.band_rows = (g.nz + bands - 1) / bands;
+  nb = (g.nz + a.band_rows - 1) / a.band_rows;
+  a.n_strips = ns;
+  a.n_bands = nb;
+  a.in = in;
+  a.out = out;
+  a.src = src;
+  a.istride = a.ostride = a.sstride = (size_t)g.nz * g.nr;
+  a.a_e = g.a_e;
+  a.a_w = g.a_w;
+  a.a_ns = g.a_ns;
+  a.a_c = g.a_c;
+  a.inv_a_c = g.inv_a_c;
+  a.active = active;
+  const size_t smem = sweep_smem_bytes(0);
+  const dim3 grd((ns * nb + kSwWPC - 1) / kSwWPC, 1, batch), blk(32 * kSwWPC, 1, 1);
+  GSB_SMEM_OPT_IN(k_jacobi_warp<T>, smem);
+  k_jacobi_warp<T><<<grd, blk, smem, st>>>(a);
   GSB_LAUNCH_CHECK();
   return GSB_OK;
 }
