@@ -391,6 +391,8 @@ int jacobi_steps_launch(gsb_ctx *ctx, double *psi, double *tmp, const double *sr
                         const int *active, cudaStream_t st);
 int jacobi_launch(const LevelGeom &g, const double *psi, const double *src, double *out, int batch,
                   const int *active, cudaStream_t st);
+int ring_apply_launch(double *f, size_t stride, const double *ring, int nz, int nr, int batch, const int *active,
+                      cudaStream_t st);
 int ring_save_launch(const double *f, size_t stride, double *ring, int nz, int nr, int batch,
                      cudaStream_t st);
 int residual_norms_launch(gsb_ctx *ctx, const LevelGeom &g, const double *psi, size_t pstride,

@@ -756,6 +756,14 @@ __global__ void k_ring_apply(double *__restrict__ f, size_t stride, const double
   else fb[(size_t)(i - 2 * nr - nz) * nr + nr - 1] = v;
 }
 
+int ring_apply_launch(double *f, size_t stride, const double *ring, int nz, int nr, int batch, const int *active,
+                      cudaStream_t st) {
+  const int rs = ring_size(nz, nr);
+  k_ring_apply<<<dim3((rs + 255) / 256, batch), 256, 0, st>>>(f, stride, ring, nz, nr, active);
+  GSB_LAUNCH_CHECK();
+  return GSB_OK;
+}
+
 int ring_save_launch(const double *f, size_t stride, double *ring, int nz, int nr, int batch,
                      cudaStream_t st) {
   const int rs = ring_size(nz, nr);

@@ -554,140 +554,107 @@ __device__ __forceinline__ double wall_or(const double *__restrict__ W, const do
   return W[(size_t)iz * nr + ir];
 }
 
-// Block = a chunk of up to 128 columns x a band of rows; a thread keeps its column and walks down the band with
-// a three-row register window of the RELAXED iterate, so a point costs three global loads (psi, Psi_new of the
-// row entering the window, the source) and one store; the east / west neighbours of the residual stencil come
-// from the adjacent lanes by warp shuffle (recomputed from memory only at the two edges of a warp).
+// A WARP owns 30 columns x a band of rows (32 lanes = the 30 columns plus one halo column on either side, whose
+// lanes only form the relaxed value for their neighbours); a lane keeps its column and walks down the band with a
+// three-row register window of the RELAXED iterate, so a point costs three global loads (psi, Psi_new of the row
+// entering the window, the source) and one store, and the east / west neighbours of the residual stencil are warp
+// shuffles with no edge cases.  The wall ring has been written into Psi_new beforehand (ring_apply_launch), so the
+// row loop has no wall logic at all.  r2's first version (column chunk x band, wall handling and warp-edge loads in
+// the loop) ran 214 instructions per point at 16 warps per SM; this one runs ~70.
+constexpr int kRxCols = 30;  // owned columns per warp
 struct RelaxPlan {
-  int cc, n_cc, n_rb;  // columns per chunk, column chunks, row bands: P = n_cc * n_rb partial blocks
+  int n_cw, n_rb, P;  // column warps, row bands, partial blocks (4 warps each) per equilibrium
 };
-static RelaxPlan relax_plan(int nz, int nr) {
+static RelaxPlan relax_plan(int nz, int nr, int batch, int num_sms) {
   RelaxPlan r;
-  r.n_cc = (nr + 127) / 128;
-  r.cc = (((nr + r.n_cc - 1) / r.n_cc) + 31) / 32 * 32;
-  r.n_cc = (nr + r.cc - 1) / r.cc;
-  r.n_rb = std::max(1, std::min(12 / r.n_cc, nz / 16));  // <= 12 partial blocks: k_decide adds them serially
+  r.n_cw = (std::max(nr - 1, 1) + kRxCols - 1) / kRxCols;  // columns 1 .. nr-1 in runs of 30; column 0 rides with the first
+  const long long want = 16LL * num_sms;               // warps to fill the GPU
+  const long long have = (long long)r.n_cw * batch;
+  r.n_rb = (int)std::max<long long>(1, std::min<long long>((want + have - 1) / have, nz / 16));
+  r.P = std::min((r.n_cw * r.n_rb + 3) / 4, kPT);
   return r;
 }
 __global__ void __launch_bounds__(128)
 k_relax(LevelGeom g, Bufs bufs, const int *__restrict__ cur, const int *__restrict__ nxt,
-        const double *__restrict__ Wall, const double *__restrict__ ringall,
-        const double *__restrict__ srcall, double alpha, double oma, double *__restrict__ rpart,
-        const int *__restrict__ active, RelaxPlan rp) {
-  __shared__ double sh[32];
-  const int b = blockIdx.y, p = blockIdx.x;
+        const double *__restrict__ Wall, const double *__restrict__ srcall, double alpha, double oma,
+        double *__restrict__ rpart, const int *__restrict__ active, RelaxPlan rp) {
+  __shared__ double sh[4][4];
+  const int b = blockIdx.y;
   if (active && !active[b]) return;
   const int nz = g.nz, nr = g.nr;
   const size_t n = (size_t)nz * nr;
-  const double *f = bufs.p[cur[b]] + b * n;
-  double *out = bufs.p[nxt[b]] + b * n;
-  const double *W = Wall + b * n;
-  const double *ring = ringall + (size_t)b * ring_size(nz, nr);
-  const double *src = srcall + b * n;
-  const int chunk = p % rp.n_cc, band = p / rp.n_cc;
-  const int ir = chunk * rp.cc + threadIdx.x;
-  const int z0 = (int)((long long)nz * band / rp.n_rb), z1 = (int)((long long)nz * (band + 1) / rp.n_rb);
-  const int lane = threadIdx.x & 31;
-  const bool col_on = ir < nr;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   double dsum = 0.0, rmax = 0.0, rsq = 0.0;
   int bad = 0;
-  // Per-thread constants hoisted out of the row loop (the kernel was instruction bound: ~240 instructions per point
-  // with index-generic wall handling): column pointers, and where this column's Psi_new comes from - the wall ring
-  // for the two wall columns (indexed by row), the ring rows for the two wall rows, the V-cycle output otherwise.
-  const int jc = col_on ? ir : nr - 1;
-  const bool wcol = jc == 0 || jc == nr - 1;
-  const double *fcol = f + jc, *wcolp = W + jc, *scol = src + jc;
-  double *ocol = out + jc;
-  const double *ring_c = ring + 2 * nr + (jc ? nz : 0);  // wall column values, [iz]
-  // Psi_new at (iz, this column); `off` = iz * nr
-  auto psi_new = [&](int iz, size_t off) -> double {
-    if (wcol) return ring_c[iz];
-    if (iz == 0) return ring[jc];
-    if (iz == nz - 1) return ring[nr + jc];
-    return wcolp[off];
-  };
-  // lanes 0 and 31 cannot get their west / east neighbour by shuffle: they fetch that column themselves
-  const bool int_col = col_on && ir > 0 && ir < nr - 1;
-  const bool edge = int_col && (lane == 0 || lane == 31);
-  const int je = lane == 0 ? jc - 1 : min(jc + 1, nr - 1);
-  const bool wcol_e = je == 0 || je == nr - 1;
-  const double *ring_e = ring + 2 * nr + (je ? nz : 0);
-  const double rs = int_col ? g.r_safe[ir] : 1.0, irs = int_col ? g.inv_r_safe[ir] : 1.0;
-  // three-row window of the relaxed iterate (1-a)*Psi + a*Psi_new (newton_solver.py:536) at this column; (Psi_new, Psi)
-  // of the centre row travel with it, so every row is loaded exactly once per thread
-  double c_m = 0.0, c_0 = 0.0, wn_0 = 0.0, old_0 = 0.0;
-  if (col_on) {
-    if (z0 > 0) {
-      const size_t o = (size_t)(z0 - 1) * nr;
-      c_m = dadd(dmul(oma, fcol[o]), dmul(alpha, psi_new(z0 - 1, o)));
-    }
-    if (z0 < z1) {
-      const size_t o = (size_t)z0 * nr;
-      wn_0 = psi_new(z0, o);
-      old_0 = fcol[o];
-      c_0 = dadd(dmul(oma, old_0), dmul(alpha, wn_0));
-    }
-  }
   constexpr int G = 4;  // rows per group: the loads of a whole group are in flight before the first use
-  size_t off = (size_t)z0 * nr;  // row offset of the group's first row
-  for (int zb = z0; zb < z1; zb += G, off += (size_t)G * nr) {  // uniform trip count over the block (shuffles)
-    double wnv[G], oldv[G], sv[G], ewn[G], eold[G];
+  const int tiles = rp.n_cw * rp.n_rb;
+  for (int tile = blockIdx.x * 4 + wid; tile < tiles; tile += rp.P * 4) {
+    const int band = tile / rp.n_cw, cw = tile - band * rp.n_cw;
+    const int col = cw * kRxCols + lane;
+    const int jc = min(col, nr - 1);  // clamped: every lane loads from a valid address
+    const bool owned = col < nr && ((lane >= 1 && lane <= kRxCols) || col == 0);
+    const bool res_col = owned && col >= 1 && col <= nr - 2;
+    const int z0 = (int)((long long)nz * band / rp.n_rb), z1 = (int)((long long)nz * (band + 1) / rp.n_rb);
+    const double *fcol = bufs.p[cur[b]] + b * n + jc;
+    const double *wcol = Wall + b * n + jc;
+    const double *scol = srcall + b * n + jc;
+    double *ocol = bufs.p[nxt[b]] + b * n + jc;
+    const double rs = res_col ? g.r_safe[col] : 1.0, irs = res_col ? g.inv_r_safe[col] : 1.0;
+    // window: relaxed values (1-a)*Psi + a*Psi_new (newton_solver.py:536) of rows iz-1, iz; (Psi_new, Psi) of row iz
+    const size_t om = (size_t)max(z0 - 1, 0) * nr, o0 = (size_t)z0 * nr;
+    double c_m = dadd(dmul(oma, fcol[om]), dmul(alpha, wcol[om]));
+    double wn_0 = wcol[o0], old_0 = fcol[o0];
+    double c_0 = dadd(dmul(oma, old_0), dmul(alpha, wn_0));
+    for (int zb = z0; zb < z1; zb += G) {
+      double wnv[G], oldv[G], sv[G];
 #pragma unroll
-    for (int u = 0; u < G; ++u) {
-      const int iz = zb + u;
-      const size_t o = off + (size_t)u * nr;
-      const bool nx = col_on && iz < z1 && iz + 1 < nz;  // row iz+1 enters the window
-      const bool ctr = iz < z1 && iz > 0 && iz < nz - 1;
-      wnv[u] = nx ? psi_new(iz + 1, o + nr) : 0.0;
-      oldv[u] = nx ? fcol[o + nr] : 0.0;
-      sv[u] = (int_col && ctr) ? scol[o] : 0.0;
-      ewn[u] = (edge && ctr) ? (wcol_e ? ring_e[iz] : W[o + je]) : 0.0;
-      eold[u] = (edge && ctr) ? f[o + je] : 0.0;
-    }
+      for (int u = 0; u < G; ++u) {  // row zb+u+1 enters the window; clamped rows are loaded and never used
+        const size_t on_ = (size_t)min(zb + u + 1, nz - 1) * nr, oc = (size_t)min(zb + u, nz - 1) * nr;
+        wnv[u] = wcol[on_];
+        oldv[u] = fcol[on_];
+        sv[u] = scol[oc];
+      }
 #pragma unroll
-    for (int u = 0; u < G; ++u) {
-      const int iz = zb + u;
-      if (iz < z1) {  // block-uniform
-        double c_p = 0.0;
-        if (col_on) {
-          // this row is the centre row now: its own statistics and its store happen here, exactly once per point
-          if (!(fabs(wn_0) <= 1.79769313486231570815e308)) bad = 1;  // NaN or +-inf
-          dsum += fabs(dsub(wn_0, old_0));
-          ocol[off + (size_t)u * nr] = c_0;
-          if (iz + 1 < nz) c_p = dadd(dmul(oma, oldv[u]), dmul(alpha, wnv[u]));
-        }
-        double c_w = __shfl_up_sync(0xffffffffu, c_0, 1), c_e = __shfl_down_sync(0xffffffffu, c_0, 1);
-        if (int_col && iz > 0 && iz < nz - 1) {
-          if (edge) {
-            const double c_edge = dadd(dmul(oma, eold[u]), dmul(alpha, ewn[u]));
-            if (lane == 0)
-              c_w = c_edge;
-            else
-              c_e = c_edge;
+      for (int u = 0; u < G; ++u) {
+        const int iz = zb + u;
+        if (iz < z1) {  // warp-uniform
+          const double c_p = dadd(dmul(oma, oldv[u]), dmul(alpha, wnv[u]));
+          if (owned) {
+            if (!(fabs(wn_0) <= 1.79769313486231570815e308)) bad = 1;  // NaN or +-inf in Psi_new
+            dsum += fabs(dsub(wn_0, old_0));
+            ocol[(size_t)iz * nr] = c_0;
           }
-          const double r = dsub(gs_apply_v(g, rs, irs, c_0, c_e, c_w, c_m, c_p), sv[u]);
-          rmax = fmax(rmax, fabs(r));
-          rsq += r * r;
+          const double c_w = __shfl_up_sync(0xffffffffu, c_0, 1), c_e = __shfl_down_sync(0xffffffffu, c_0, 1);
+          if (res_col && iz > 0 && iz < nz - 1) {
+            const double r = dsub(gs_apply_v(g, rs, irs, c_0, c_e, c_w, c_m, c_p), sv[u]);
+            rmax = fmax(rmax, fabs(r));
+            rsq += r * r;
+          }
+          c_m = c_0;
+          c_0 = c_p;
+          wn_0 = wnv[u];
+          old_0 = oldv[u];
         }
-        c_m = c_0;
-        c_0 = c_p;
-        wn_0 = wnv[u];
-        old_0 = oldv[u];
       }
     }
   }
-  const int anybad = __syncthreads_or(bad);
-  dsum = block_sum(dsum, sh);
+  dsum = warp_sum(dsum);
+  rmax = warp_max(rmax);
+  rsq = warp_sum(rsq);
+  bad = __any_sync(0xffffffffu, bad);
+  if (lane == 0) {
+    sh[wid][0] = dsum;
+    sh[wid][1] = bad ? 1.0 : 0.0;
+    sh[wid][2] = rmax;
+    sh[wid][3] = rsq;
+  }
   __syncthreads();
-  rmax = block_max(rmax, sh);
-  __syncthreads();
-  rsq = block_sum(rsq, sh);
   if (threadIdx.x == 0) {
-    double *o = rpart + ((size_t)b * kPT + p) * kRW;
-    o[0] = dsum;
-    o[1] = anybad ? 1.0 : 0.0;
-    o[2] = rmax;
-    o[3] = rsq;
+    double *o = rpart + ((size_t)b * kPT + blockIdx.x) * kRW;
+    o[0] = ((sh[0][0] + sh[1][0]) + sh[2][0]) + sh[3][0];
+    o[1] = (sh[0][1] + sh[1][1] + sh[2][1] + sh[3][1]) > 0.0 ? 1.0 : 0.0;
+    o[2] = fmax(fmax(sh[0][2], sh[1][2]), fmax(sh[2][2], sh[3][2]));
+    o[3] = ((sh[0][3] + sh[1][3]) + sh[2][3]) + sh[3][3];
   }
 }
 
@@ -2306,7 +2273,7 @@ static int picard_solve_impl(gsb_ctx *ctx, const gsb_picard_params *p, double *p
     mixb.fallback = w->and_fb;
   }
   const double oma = 1.0 - p->alpha;
-  const RelaxPlan rplan = relax_plan(nz, nr);
+  const RelaxPlan rplan = relax_plan(nz, nr, batch, ctx->num_sms);
   const int check_every = p->check_every > 0 ? p->check_every : 8;
   volatile double dr2 = ctx->dr * ctx->dr, dz2 = ctx->dz * ctx->dz, f1 = 4.0 * ctx->dr, f2 = f1 * ctx->dz;
   // one Picard iteration of every active equilibrium; `poll`: reset the active counter before the decision and
@@ -2344,8 +2311,12 @@ static int picard_solve_impl(gsb_ctx *ctx, const gsb_picard_params *p, double *p
       k_jacobi_from_cur<<<grd, blk, 0, st>>>(g, bufs, s.cur, w->source, w->W, s.active);
       GSB_LAUNCH_CHECK();
     }
-    k_relax<<<dim3(rplan.n_cc * rplan.n_rb, batch), rplan.cc, 0, st>>>(g, bufs, s.cur, s.nxt, w->W, w->ring, w->source, p->alpha,
-                                                                      oma, w->rpart, s.active, rplan);
+    {  // Psi_new's wall = the boundary map (copy_wall, newton_solver.py:514 via _elliptic_solve): written into W
+      int r2 = ring_apply_launch(w->W, n, w->ring, nz, nr, batch, s.active, st);
+      if (r2) return r2;
+    }
+    k_relax<<<dim3(rplan.P, batch), 128, 0, st>>>(g, bufs, s.cur, s.nxt, w->W, w->source, p->alpha, oma, w->rpart, s.active,
+                                                  rplan);
     GSB_LAUNCH_CHECK();
     if (p->method == 3) {  // every kernel decides on the device whether this is a mixing iteration
       const int blocks = (int)std::min<size_t>((n + 255) / 256, 256);
@@ -2359,11 +2330,11 @@ static int picard_solve_impl(gsb_ctx *ctx, const gsb_picard_params *p, double *p
       GSB_LAUNCH_CHECK();
       k_and_mix<<<dim3(blocks, batch), 256, 0, st>>>(mixb, bufs, s.nxt, s.iter, w->ring, nz, nr, s.active);
       GSB_LAUNCH_CHECK();
-      k_and_gs<<<dim3(rplan.n_cc * rplan.n_rb, batch), 256, 0, st>>>(g, bufs, s.nxt, s.iter, w->source, w->rpart, s.active);
+      k_and_gs<<<dim3(rplan.P, batch), 256, 0, st>>>(g, bufs, s.nxt, s.iter, w->source, w->rpart, s.active);
       GSB_LAUNCH_CHECK();
     }
     if (poll) GSB_CUDA(cudaMemsetAsync(ctx->counter, 0, sizeof(int), st));
-    k_decide<<<(batch + 127) / 128, 128, 0, st>>>(s, w->rpart, rplan.n_cc * rplan.n_rb, (double)n, (double)(nz - 2) * (double)(nr - 2), p->tol,
+    k_decide<<<(batch + 127) / 128, 128, 0, st>>>(s, w->rpart, rplan.P, (double)n, (double)(nz - 2) * (double)(nr - 2), p->tol,
                                                   p->require_gs_residual, p->gs_tol, p->max_iterations, hist_dev,
                                                   gs_hist_dev, ctx->counter, batch);
     GSB_LAUNCH_CHECK();
