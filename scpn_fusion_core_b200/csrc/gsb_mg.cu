@@ -449,12 +449,21 @@ k_prolong_add(const double *__restrict__ ec, int nzc, int nrc, double *__restric
   const int b = blockIdx.z;
   if (active && !active[b]) return;
   const int ir = 1 + blockIdx.x * blockDim.x + threadIdx.x;
-  const int iz = 1 + blockIdx.y * blockDim.y + threadIdx.y;
-  if (iz >= nzf - 1 || ir >= nrf - 1) return;
-  double v;
-  prolong_value(ec + (size_t)b * nzc * nrc, nzc, nrc, nzf, nrf, iz, ir, v);
-  double *p = psi + (size_t)b * pstride + (size_t)iz * nrf + ir;
-  p[0] = dadd(p[0], v);
+  const int iz0 = 1 + 4 * (blockIdx.y * blockDim.y + threadIdx.y);  // four rows per thread: four fine loads in flight
+  if (iz0 >= nzf - 1 || ir >= nrf - 1) return;
+  double *p = psi + (size_t)b * pstride + (size_t)iz0 * nrf + ir;
+  const double *c = ec + (size_t)b * nzc * nrc;
+  double old[4], v[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) old[k] = (iz0 + k < nzf - 1) ? p[(size_t)k * nrf] : 0.0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    v[k] = 0.0;
+    if (iz0 + k < nzf - 1) prolong_value(c, nzc, nrc, nzf, nrf, iz0 + k, ir, v[k]);
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (iz0 + k < nzf - 1) p[(size_t)k * nrf] = dadd(old[k], v[k]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -705,7 +714,7 @@ int vcycle_launch(gsb_ctx *ctx, double *psi, size_t psi_stride, const double *sr
     const LevelGeom &c = ctx->levels[l + 1].g;
     double *cur = curv[l] ? curv[l] : X(l);
     if (g.nz > 2 && g.nr > 2) {
-      const dim3 grd((g.nr - 2 + 31) / 32, (g.nz - 2 + 7) / 8, batch);
+      const dim3 grd((g.nr - 2 + 31) / 32, (g.nz - 2 + 31) / 32, batch);  // 32 x 8 threads, four rows each
       k_prolong_add<<<grd, blk, 0, st>>>(ctx->levels[l + 1].e, c.nz, c.nr, cur, XS(l), g.nz, g.nr, active);
       GSB_LAUNCH_CHECK();
     }

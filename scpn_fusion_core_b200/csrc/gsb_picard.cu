@@ -499,13 +499,22 @@ k_source_scale(size_t n, int nz, int nr, double dr, double dz, const double *__r
   const double sc = ok ? __ddiv_rn(ip[b], icur) : 0.0;
   if (scale_out && p == 0 && threadIdx.x == 0) scale_out[b] = sc;
   const int r0 = (int)((long long)nz * p / gridDim.x), r1 = (int)((long long)nz * (p + 1) / gridDim.x);
-  for (int idx = threadIdx.x; idx < (r1 - r0) * nr; idx += blockDim.x) {
-    const int iz = r0 + idx / nr, ir = idx % nr;
-    const size_t o = (size_t)b * n + (size_t)iz * nr + ir;
-    const double j = ok ? dmul(jphi[o], sc) : 0.0;
-    jphi[o] = j;
-    if (source) source[o] = dmul(mr[ir], j);  // (-mu0*R)*J
-  }
+  // threads across columns, four rows per trip with their loads issued together (no integer division, 4 loads in flight)
+  for (int iz = r0; iz < r1; iz += 4)
+    for (int ir = threadIdx.x; ir < nr; ir += blockDim.x) {
+      const size_t o = (size_t)b * n + (size_t)iz * nr + ir;
+      const double m = mr[ir];
+      double jv[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) jv[k] = (iz + k < r1) ? jphi[o + (size_t)k * nr] : 0.0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (iz + k < r1) {
+          const double j = ok ? dmul(jv[k], sc) : 0.0;
+          jphi[o + (size_t)k * nr] = j;
+          if (source) source[o + (size_t)k * nr] = dmul(m, j);  // (-mu0*R)*J
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------- E helpers
@@ -516,8 +525,16 @@ k_copy_from_cur(Bufs bufs, const int *__restrict__ cur, size_t n, double *__rest
   if (active && !active[b]) return;
   const double *f = bufs.p[cur ? cur[b] : 0] + (size_t)b * n;
   double *d = dst + (size_t)b * n;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-    d[i] = do_sanitize ? sanitize(f[i]) : f[i];
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n; i += 4 * stride) {  // four independent loads in flight per thread
+    const double v0 = f[i], v1 = f[i + stride], v2 = f[i + 2 * stride], v3 = f[i + 3 * stride];
+    d[i] = do_sanitize ? sanitize(v0) : v0;
+    d[i + stride] = do_sanitize ? sanitize(v1) : v1;
+    d[i + 2 * stride] = do_sanitize ? sanitize(v2) : v2;
+    d[i + 3 * stride] = do_sanitize ? sanitize(v3) : v3;
+  }
+  for (; i < n; i += stride) d[i] = do_sanitize ? sanitize(f[i]) : f[i];
 }
 
 __global__ void __launch_bounds__(256)
@@ -568,7 +585,7 @@ struct RelaxPlan {
 static RelaxPlan relax_plan(int nz, int nr, int batch, int num_sms) {
   RelaxPlan r;
   r.n_cw = (std::max(nr - 1, 1) + kRxCols - 1) / kRxCols;  // columns 1 .. nr-1 in runs of 30; column 0 rides with the first
-  const long long want = 16LL * num_sms;               // warps to fill the GPU
+  const long long want = 64LL * num_sms;               // a few waves of resident warps: the kernel is load-latency bound
   const long long have = (long long)r.n_cw * batch;
   r.n_rb = (int)std::max<long long>(1, std::min<long long>((want + have - 1) / have, nz / 16));
   r.P = std::min((r.n_cw * r.n_rb + 3) / 4, kPT);
