@@ -1,21 +1,25 @@
 // gsb_sweep.cu - temporally blocked streaming RB-SOR: S full sweeps (2S colour passes) of mg_smooth
-// (multigrid_solve.py:148-208) in ONE pass over HBM.
+// (multigrid_solve.py:148-208) in ONE pass over HBM; and the same for T Jacobi steps (k_jacobi_warp, the Picard seed).
 //
 // The per-colour streaming kernel (k_smooth_colour) moves psi twice and the source once per
 // colour pass: 48 B of DRAM traffic per point per sweep for 24 algorithmic bytes.  Here every WARP
 // owns a 64-column strip of one row band of one equilibrium and marches down the rows on its own:
-// no CTA barrier anywhere, only __syncwarp.  The warp keeps a private ring of rows in shared memory
-// (filled by cp.async three rows ahead); lane k holds the column pair (2k, 2k+1).  Colour pass t
+// no CTA barrier anywhere, only __syncwarp; lane k holds the column pair (2k, 2k+1).  Colour pass t
 // (= stage t) works two rows behind pass t-1, so the 2S stages of a step are mutually independent:
 //   stage t at row r = i - 2t reads rows r-1, r, r+1: pass t-1 finished r+1 one step earlier, and
 //   pass t+1 (row r-2) touches nothing stage t reads;
-// a lane therefore loads the operands of all 2S stages, computes 2S independent updates (ILP = 2S
-// hides the FP64 latency) and stores them, once per row step.
+// a lane therefore gathers the operands of all 2S stages, computes 2S independent updates (ILP = 2S
+// hides the FP64 latency) and hands them on, once per row step.
 // Strips/bands overlap by 2S columns/rows; the overlap is recomputed (an update is valid t+1 points
 // inside the tile edge after pass t) and only tile interiors are written, so with more than one
 // tile per equilibrium the sweep is out of place (neighbours read each other's interiors).
-// The ring keeps each row as two half rows (even / odd columns) so operands are unit-stride across
-// the lanes.  Arithmetic: the same operand order as sor_point (bit-identical results).
+// Two bodies implement this (bit-identical):
+//   sweep_warp_body_rc (default)  the lane's own values travel in registers, the shared-memory ring (rows as two half
+//                                 rows, even / odd columns, filled by cp.async) is landing zone + neighbour mailbox;
+//   sweep_warp_body               every operand is read from the ring (the r1 / early r2 form, kept as the measured
+//                                 comparison: GSB_SWEEP_UNROLL=2|4).
+// Arithmetic: the same operand order as sor_point (bit-identical results).  History and captures:
+// profiles/r2_sweep_icache.md.
 #include "gsb_internal.cuh"
 
 namespace gsb {
