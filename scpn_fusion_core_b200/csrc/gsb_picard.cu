@@ -108,21 +108,29 @@ k_topo(Bufs bufs, const int *__restrict__ cur, size_t n, int nz, int nr, GradGeo
   const int r0 = (int)((long long)nz * p / P), r1 = (int)((long long)nz * (p + 1) / P);
   ValIdx mx{0.0, -1}, mb{0.0, -1};
   double mn = INFINITY;
-  // rows of the block's band one at a time, threads across the columns: no integer division per point, the
-  // divertor-row test is uniform over the block, and a thread meets its points in increasing flat index
-#pragma unroll 4
-  for (int iz = r0; iz < r1; ++iz) {
-    const bool masked = rowmask[iz] != 0;
-    for (int ir = threadIdx.x; ir < nr; ir += blockDim.x) {
-      const int flat = iz * nr + ir;
+  // the block's band as one flat index range, (row, column) carried along without a division per point: every thread
+  // is busy whatever nr is (a column-strided row loop leaves ONE thread working in its last trip at nr = 2^k + 1),
+  // and a thread meets its points in increasing flat index
+  {
+    const int step = blockDim.x, sq = step / nr, sm = step - sq * nr;
+    int iz = r0 + (int)threadIdx.x / nr, ir = (int)threadIdx.x - ((int)threadIdx.x / nr) * nr;
+    const int end = r1 * nr;
+#pragma unroll 2
+    for (int flat = r0 * nr + (int)threadIdx.x; flat < end; flat += step) {
       const double v = f[flat];
       if (mx.i < 0 || v > mx.v) mx = ValIdx{v, flat};  // strict >: the first maximum of this thread's sequence stays
       mn = fmin(mn, v);
-      if (masked) {
+      if (rowmask[iz] != 0) {
         double gz, gr;
         grad_point(f, nz, nr, iz, ir, gg, gz, gr);
         const double bm = hypot_glibc(gr, gz);
         if (isfinite(bm) && (mb.i < 0 || bm < mb.v)) mb = ValIdx{bm, flat};
+      }
+      ir += sm;
+      iz += sq;
+      if (ir >= nr) {
+        ir -= nr;
+        ++iz;
       }
     }
   }
@@ -459,11 +467,11 @@ k_source_raw(Bufs bufs, const int *__restrict__ cur, size_t n, int nz, int nr,
   const bool same_prof = pp[0] == pf[0] && pp[1] == pf[1] && pp[2] == pf[2] && pp[3] == pf[3];
   const int r0 = (int)((long long)nz * p / P), r1 = (int)((long long)nz * (p + 1) / P);
   double acc = 0.0;
-  // rows of the block's band one at a time, threads across the columns (no integer division per point)
+  // the block's band as one flat index range with the column carried along (every thread busy whatever nr is)
+  const int step = blockDim.x, sm = step % nr;
+  int ir = (int)threadIdx.x % nr;
 #pragma unroll 2
-  for (int iz = r0; iz < r1; ++iz)
-    for (int ir = threadIdx.x; ir < nr; ir += blockDim.x) {
-      const size_t o = (size_t)iz * nr + ir;
+  for (size_t o = (size_t)r0 * nr + threadIdx.x; o < (size_t)r1 * nr; o += step, ir = (ir + sm >= nr) ? ir + sm - nr : ir + sm) {
       const double pn = ddiv_yf(dsub(f[o], psi_ax), denom, inv_denom);
       const bool in = (pn >= 0.0) && (pn < 1.0);
       double pr = 0.0, ff = 0.0;
@@ -499,22 +507,28 @@ k_source_scale(size_t n, int nz, int nr, double dr, double dz, const double *__r
   const double sc = ok ? __ddiv_rn(ip[b], icur) : 0.0;
   if (scale_out && p == 0 && threadIdx.x == 0) scale_out[b] = sc;
   const int r0 = (int)((long long)nz * p / gridDim.x), r1 = (int)((long long)nz * (p + 1) / gridDim.x);
-  // threads across columns, four rows per trip with their loads issued together (no integer division, 4 loads in flight)
-  for (int iz = r0; iz < r1; iz += 4)
-    for (int ir = threadIdx.x; ir < nr; ir += blockDim.x) {
-      const size_t o = (size_t)b * n + (size_t)iz * nr + ir;
-      const double m = mr[ir];
-      double jv[4];
+  // the block's band as one flat index range, four elements per trip with their loads issued together; the column
+  // index is carried along (no division per point, every thread busy whatever nr is)
+  const int step = blockDim.x, sm = step % nr;
+  int ir = (int)threadIdx.x % nr;
+  const size_t base = (size_t)b * n, end = (size_t)r1 * nr;
+  for (size_t o = (size_t)r0 * nr + threadIdx.x; o < end; o += (size_t)4 * step) {
+    double jv[4];
+    int irk[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) jv[k] = (iz + k < r1) ? jphi[o + (size_t)k * nr] : 0.0;
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (iz + k < r1) {
-          const double j = ok ? dmul(jv[k], sc) : 0.0;
-          jphi[o + (size_t)k * nr] = j;
-          if (source) source[o + (size_t)k * nr] = dmul(m, j);  // (-mu0*R)*J
-        }
+    for (int k = 0; k < 4; ++k) {
+      irk[k] = ir;
+      ir = (ir + sm >= nr) ? ir + sm - nr : ir + sm;
+      jv[k] = (o + (size_t)k * step < end) ? jphi[base + o + (size_t)k * step] : 0.0;
     }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (o + (size_t)k * step < end) {
+        const double j = ok ? dmul(jv[k], sc) : 0.0;
+        jphi[base + o + (size_t)k * step] = j;
+        if (source) source[base + o + (size_t)k * step] = dmul(mr[irk[k]], j);  // (-mu0*R)*J
+      }
+  }
 }
 
 // ---------------------------------------------------------------------------- E helpers
