@@ -711,20 +711,14 @@ int jacobi_fused_launch(const LevelGeom &g, const double *in, double *out, const
   SweepArgs a{};
   a.nz = g.nz;
   a.nr = g.nr;
-  int ns, nb, sc;
   // strips of 64 - 2T interior columns; bands as for the sweeps (T halo rows per side)
   const int step = kSwCols - 2 * T;
-  if (g.nr <= kSwCols) {
-    ns = 1;
-  } else {
-    ns = (g.nr + step - 1) / step;
-  }
-  (void)sc;
+  const int ns = g.nr <= kSwCols ? 1 : (g.nr + step - 1) / step;
   const long long warps = (long long)ns * batch, want = 24LL * num_sms;
   int bands = 1;
   if (warps < want) bands = (int)std::min<long long>((want + warps - 1) / warps, std::max(1, g.nz / 8));
   a.band_rows = (g.nz + bands - 1) / bands;
-  nb = (g.nz + a.band_rows - 1) / a.band_rows;
+  const int nb = (g.nz + a.band_rows - 1) / a.band_rows;
   a.n_strips = ns;
   a.n_bands = nb;
   a.in = in;
